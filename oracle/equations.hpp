@@ -1,0 +1,518 @@
+// TEST INFRASTRUCTURE ONLY -- CPU oracle ("parity unpinned", see basis.hpp header).
+//
+// Equations, two-point / surface fluxes, initial conditions and source terms that the reference passes
+// through from Trixi.jl as Julia callables into its kernels:
+//   volume_flux(u_node,u_node1,1,equations)        /root/reference/src/solvers/dg_3d_kernel.jl:226-234
+//   flux(u_node,1,equations)                        /root/reference/src/solvers/dg_3d_kernel.jl:93-95
+//   surface_flux(u_ll,u_rr,orientation,equations)   /root/reference/src/solvers/dg_3d_kernel.jl:1166
+//   nonconservative_flux(...)                       /root/reference/src/solvers/dg_3d_kernel.jl:387-395,1190-1191
+//   max_abs_speeds                                  /root/reference/src/callbacks_step/stepsize_dg_3d.jl:34
+// Formulas restate Trixi.jl. Templated on the scalar so an op-counting
+// scalar can be substituted for `double`.
+#pragma once
+#include <cmath>
+#include <algorithm>
+
+namespace orc {
+
+enum EqKind { EQ_ADVECTION = 0, EQ_EULER = 1, EQ_MHD = 2 };
+enum FluxKind {
+  FLUX_CENTRAL = 0,
+  FLUX_LAX_FRIEDRICHS = 1,        // FluxLaxFriedrichs(max_abs_speed)       (Trixi 0.13 default)
+  FLUX_LAX_FRIEDRICHS_NAIVE = 2,  // FluxLaxFriedrichs(max_abs_speed_naive) (Trixi <= 0.12 default)
+  FLUX_HLL = 3,                   // FluxHLL(min_max_speed_davis)           (Trixi 0.13 default)
+  FLUX_HLL_NAIVE = 4,             // FluxHLL(min_max_speed_naive)
+  FLUX_RANOCHA = 5,
+  FLUX_SHIMA_ETAL = 6,
+  FLUX_HINDENLANG_GASSNER = 7,
+  FLUX_HLLE = 8,                  // FluxHLL(min_max_speed_einfeldt)
+  FLUX_NONE = -1
+};
+enum ICKind {
+  IC_CONSTANT = 0, IC_CONVERGENCE_TEST = 1, IC_WEAK_BLAST_WAVE = 2, IC_DENSITY_WAVE = 3
+};
+enum SourceKind { SRC_NONE = 0, SRC_CONVERGENCE_TEST = 1 };
+
+struct EqParams {
+  int kind = EQ_EULER;
+  int ndim = 3;
+  int nvars = 5;
+  double gamma = 1.4;
+  double advection_velocity[3] = {1, 1, 1};
+  double c_h = 1.0;  // GLM cleaning speed (equations.c_h; set by GlmSpeedCallback in Trixi)
+};
+
+template <class T> inline T sq(T x) { return x * x; }
+
+// Trixi `ln_mean` / `inv_ln_mean` (math.jl), Ismail-Roe / Ranocha series for small differences
+template <class T> inline T ln_mean(T x, T y) {
+  const double epsilon_f2 = 1.0e-4;
+  T f2 = (x * (x - 2 * y) + y * y) / (x * (x + 2 * y) + y * y);
+  if (f2 < epsilon_f2) return (x + y) / (2 + f2 * (2.0 / 3 + f2 * (2.0 / 5 + f2 * (2.0 / 7))));
+  return (y - x) / log(y / x);
+}
+template <class T> inline T inv_ln_mean(T x, T y) {
+  const double epsilon_f2 = 1.0e-4;
+  T f2 = (x * (x - 2 * y) + y * y) / (x * (x + 2 * y) + y * y);
+  if (f2 < epsilon_f2) return (2 + f2 * (2.0 / 3 + f2 * (2.0 / 5 + f2 * (2.0 / 7)))) / (x + y);
+  return log(y / x) / (y - x);
+}
+
+// ---------------------------------------------------------------------------------------------
+// Linear scalar advection
+// ---------------------------------------------------------------------------------------------
+template <class T> struct Advection {
+  static void flux(const T* u, int o, const EqParams& p, T* f) { f[0] = p.advection_velocity[o - 1] * u[0]; }
+  static void max_abs_speeds(const T*, const EqParams& p, T* lam) {
+    for (int d = 0; d < p.ndim; ++d) lam[d] = std::fabs(p.advection_velocity[d]);
+  }
+  static bool two_point(int kind, const T* ul, const T* ur, int o, const EqParams& p, T* f) {
+    double a = p.advection_velocity[o - 1];
+    switch (kind) {
+      case FLUX_CENTRAL: f[0] = 0.5 * (a * ul[0] + a * ur[0]); return true;
+      case FLUX_LAX_FRIEDRICHS:
+      case FLUX_LAX_FRIEDRICHS_NAIVE: {
+        T lam = std::fabs(a);
+        f[0] = 0.5 * (a * ul[0] + a * ur[0]) - 0.5 * lam * (ur[0] - ul[0]);
+        return true;
+      }
+      default: return false;
+    }
+  }
+};
+
+// ---------------------------------------------------------------------------------------------
+// Compressible Euler, ndim = 1,2,3; variables (rho, rho_v[ndim], rho_e)
+// ---------------------------------------------------------------------------------------------
+template <class T> struct Euler {
+  static void cons2prim(const T* u, const EqParams& p, T* q) {  // (rho, v..., p)
+    int nd = p.ndim;
+    T rho = u[0];
+    T ke = 0;
+    for (int d = 0; d < nd; ++d) { q[1 + d] = u[1 + d] / rho; ke += u[1 + d] * q[1 + d]; }
+    q[0] = rho;
+    q[nd + 1] = (p.gamma - 1) * (u[nd + 1] - 0.5 * ke);
+  }
+  static void flux(const T* u, int o, const EqParams& p, T* f) {
+    int nd = p.ndim;
+    T q[5];
+    cons2prim(u, p, q);
+    T v = q[o];
+    f[0] = u[o];
+    for (int d = 0; d < nd; ++d) f[1 + d] = u[o] * q[1 + d];
+    f[o] += q[nd + 1];
+    f[nd + 1] = (u[nd + 1] + q[nd + 1]) * v;
+  }
+  static void max_abs_speeds(const T* u, const EqParams& p, T* lam) {
+    T q[5];
+    cons2prim(u, p, q);
+    T c = sqrt(p.gamma * q[p.ndim + 1] / q[0]);
+    for (int d = 0; d < p.ndim; ++d) lam[d] = fabs(q[1 + d]) + c;
+  }
+  static T max_abs_speed(bool naive, const T* ul, const T* ur, int o, const EqParams& p) {
+    T ql[5], qr[5];
+    cons2prim(ul, p, ql); cons2prim(ur, p, qr);
+    T cl = sqrt(p.gamma * ql[p.ndim + 1] / ql[0]);
+    T cr = sqrt(p.gamma * qr[p.ndim + 1] / qr[0]);
+    T vl = fabs(ql[o]), vr = fabs(qr[o]);
+    if (naive) return std::max(vl, vr) + std::max(cl, cr);
+    return std::max(vl + cl, vr + cr);
+  }
+  static void min_max_speed(bool naive, const T* ul, const T* ur, int o, const EqParams& p, T& lmin, T& lmax) {
+    T ql[5], qr[5];
+    cons2prim(ul, p, ql); cons2prim(ur, p, qr);
+    T cl = sqrt(p.gamma * ql[p.ndim + 1] / ql[0]);
+    T cr = sqrt(p.gamma * qr[p.ndim + 1] / qr[0]);
+    if (naive) { lmin = ql[o] - cl; lmax = qr[o] + cr; }
+    else { lmin = std::min(ql[o] - cl, qr[o] - cr); lmax = std::max(ql[o] + cl, qr[o] + cr); }
+  }
+  static bool two_point(int kind, const T* ul, const T* ur, int o, const EqParams& p, T* f) {
+    const int nd = p.ndim, nv = nd + 2;
+    switch (kind) {
+      case FLUX_CENTRAL: {
+        T fl[5], fr[5];
+        flux(ul, o, p, fl); flux(ur, o, p, fr);
+        for (int v = 0; v < nv; ++v) f[v] = 0.5 * (fl[v] + fr[v]);
+        return true;
+      }
+      case FLUX_LAX_FRIEDRICHS:
+      case FLUX_LAX_FRIEDRICHS_NAIVE: {
+        T fl[5], fr[5];
+        flux(ul, o, p, fl); flux(ur, o, p, fr);
+        T lam = max_abs_speed(kind == FLUX_LAX_FRIEDRICHS_NAIVE, ul, ur, o, p);
+        for (int v = 0; v < nv; ++v) f[v] = 0.5 * (fl[v] + fr[v]) + (-0.5 * lam * (ur[v] - ul[v]));
+        return true;
+      }
+      case FLUX_HLL:
+      case FLUX_HLL_NAIVE: {
+        T lmin, lmax;
+        min_max_speed(kind == FLUX_HLL_NAIVE, ul, ur, o, p, lmin, lmax);
+        if (lmin >= 0 && lmax >= 0) { flux(ul, o, p, f); return true; }
+        if (lmax <= 0 && lmin <= 0) { flux(ur, o, p, f); return true; }
+        T fl[5], fr[5];
+        flux(ul, o, p, fl); flux(ur, o, p, fr);
+        T inv = 1.0 / (lmax - lmin);
+        T fac_ll = lmax * inv, fac_rr = lmin * inv, fac_d = lmin * lmax * inv;
+        for (int v = 0; v < nv; ++v) f[v] = fac_ll * fl[v] - fac_rr * fr[v] + fac_d * (ur[v] - ul[v]);
+        return true;
+      }
+      case FLUX_RANOCHA: {
+        T ql[5], qr[5];
+        cons2prim(ul, p, ql); cons2prim(ur, p, qr);
+        T rho_ll = ql[0], rho_rr = qr[0], p_ll = ql[nd + 1], p_rr = qr[nd + 1];
+        T rho_mean = ln_mean(rho_ll, rho_rr);
+        T inv_rho_p_mean = p_ll * p_rr * inv_ln_mean(rho_ll * p_rr, rho_rr * p_ll);
+        T vavg[3], vsq = 0;
+        for (int d = 0; d < nd; ++d) { vavg[d] = 0.5 * (ql[1 + d] + qr[1 + d]); vsq += ql[1 + d] * qr[1 + d]; }
+        T p_avg = 0.5 * (p_ll + p_rr);
+        T velocity_square_avg = 0.5 * vsq;
+        f[0] = rho_mean * vavg[o - 1];
+        for (int d = 0; d < nd; ++d) f[1 + d] = f[0] * vavg[d];
+        f[o] += p_avg;
+        f[nd + 1] = f[0] * (velocity_square_avg + inv_rho_p_mean / (p.gamma - 1)) +
+                    0.5 * (p_ll * qr[o] + p_rr * ql[o]);
+        return true;
+      }
+      case FLUX_SHIMA_ETAL: {
+        T ql[5], qr[5];
+        cons2prim(ul, p, ql); cons2prim(ur, p, qr);
+        T rho_avg = 0.5 * (ql[0] + qr[0]);
+        T p_avg = 0.5 * (ql[nd + 1] + qr[nd + 1]);
+        T vavg[3], vsq = 0;
+        for (int d = 0; d < nd; ++d) { vavg[d] = 0.5 * (ql[1 + d] + qr[1 + d]); vsq += ql[1 + d] * qr[1 + d]; }
+        T kin_avg = 0.5 * vsq;
+        T pv_avg = 0.5 * (ql[nd + 1] * qr[o] + qr[nd + 1] * ql[o]);
+        f[0] = rho_avg * vavg[o - 1];
+        for (int d = 0; d < nd; ++d) f[1 + d] = f[0] * vavg[d];
+        f[o] += p_avg;
+        f[nd + 1] = p_avg * vavg[o - 1] / (p.gamma - 1) + f[0] * kin_avg + pv_avg;
+        return true;
+      }
+      default: return false;
+    }
+  }
+};
+
+// ---------------------------------------------------------------------------------------------
+// Ideal GLM-MHD 3D: (rho, rho_v1..3, rho_e, B1..3, psi)
+// ---------------------------------------------------------------------------------------------
+template <class T> struct Mhd3D {
+  static void cons2prim(const T* u, const EqParams& p, T* q) {
+    T rho = u[0];
+    T v1 = u[1] / rho, v2 = u[2] / rho, v3 = u[3] / rho;
+    T pr = (p.gamma - 1) * (u[4] - 0.5 * (u[1] * v1 + u[2] * v2 + u[3] * v3) -
+                            0.5 * (u[5] * u[5] + u[6] * u[6] + u[7] * u[7]) - 0.5 * u[8] * u[8]);
+    q[0] = rho; q[1] = v1; q[2] = v2; q[3] = v3; q[4] = pr; q[5] = u[5]; q[6] = u[6]; q[7] = u[7]; q[8] = u[8];
+  }
+  static void flux(const T* u, int o, const EqParams& p, T* f) {
+    T rho = u[0], rho_e = u[4], B1 = u[5], B2 = u[6], B3 = u[7], psi = u[8];
+    T v1 = u[1] / rho, v2 = u[2] / rho, v3 = u[3] / rho;
+    T kin_en = 0.5 * (u[1] * v1 + u[2] * v2 + u[3] * v3);
+    T mag_en = 0.5 * (B1 * B1 + B2 * B2 + B3 * B3);
+    T p_over_gm1 = (rho_e - kin_en - mag_en - 0.5 * psi * psi);
+    T pr = (p.gamma - 1) * p_over_gm1;
+    T vdotB = v1 * B1 + v2 * B2 + v3 * B3;
+    T en = kin_en + p.gamma * p_over_gm1 + 2 * mag_en;
+    if (o == 1) {
+      f[0] = u[1]; f[1] = u[1] * v1 + pr + mag_en - B1 * B1; f[2] = u[1] * v2 - B1 * B2; f[3] = u[1] * v3 - B1 * B3;
+      f[4] = en * v1 - B1 * vdotB + p.c_h * psi * B1;
+      f[5] = p.c_h * psi; f[6] = v1 * B2 - v2 * B1; f[7] = v1 * B3 - v3 * B1; f[8] = p.c_h * B1;
+    } else if (o == 2) {
+      f[0] = u[2]; f[1] = u[2] * v1 - B2 * B1; f[2] = u[2] * v2 + pr + mag_en - B2 * B2; f[3] = u[2] * v3 - B2 * B3;
+      f[4] = en * v2 - B2 * vdotB + p.c_h * psi * B2;
+      f[5] = v2 * B1 - v1 * B2; f[6] = p.c_h * psi; f[7] = v2 * B3 - v3 * B2; f[8] = p.c_h * B2;
+    } else {
+      f[0] = u[3]; f[1] = u[3] * v1 - B3 * B1; f[2] = u[3] * v2 - B3 * B2; f[3] = u[3] * v3 + pr + mag_en - B3 * B3;
+      f[4] = en * v3 - B3 * vdotB + p.c_h * psi * B3;
+      f[5] = v3 * B1 - v1 * B3; f[6] = v3 * B2 - v2 * B3; f[7] = p.c_h * psi; f[8] = p.c_h * B3;
+    }
+  }
+  static T fast_wavespeed(const T* u, int o, const EqParams& p) {
+    T rho = u[0];
+    T v1 = u[1] / rho, v2 = u[2] / rho, v3 = u[3] / rho;
+    T kin_en = 0.5 * (u[1] * v1 + u[2] * v2 + u[3] * v3);
+    T mag_en = 0.5 * (u[5] * u[5] + u[6] * u[6] + u[7] * u[7]);
+    T pr = (p.gamma - 1) * (u[4] - kin_en - mag_en - 0.5 * u[8] * u[8]);
+    T a_square = p.gamma * pr / rho;
+    T sqrt_rho = sqrt(rho);
+    T b1 = u[5] / sqrt_rho, b2 = u[6] / sqrt_rho, b3 = u[7] / sqrt_rho;
+    T b_square = b1 * b1 + b2 * b2 + b3 * b3;
+    T bo = (o == 1) ? b1 : (o == 2 ? b2 : b3);
+    return sqrt(0.5 * (a_square + b_square) + 0.5 * sqrt(sq(a_square + b_square) - 4.0 * a_square * bo * bo));
+  }
+  static void max_abs_speeds(const T* u, const EqParams& p, T* lam) {
+    for (int d = 0; d < 3; ++d) lam[d] = fabs(u[1 + d] / u[0]) + fast_wavespeed(u, d + 1, p);
+  }
+  // Roe-averaged fast speed (Cargo & Gallice 1997), Trixi `calc_fast_wavespeed_roe`
+  static void fast_wavespeed_roe(const T* ul, const T* ur, int o, const EqParams& p, T& vel_out, T& c_f) {
+    T rho_ll = ul[0], rho_rr = ur[0];
+    T v1l = ul[1] / rho_ll, v2l = ul[2] / rho_ll, v3l = ul[3] / rho_ll;
+    T v1r = ur[1] / rho_rr, v2r = ur[2] / rho_rr, v3r = ur[3] / rho_rr;
+    T kin_l = 0.5 * (ul[1] * v1l + ul[2] * v2l + ul[3] * v3l);
+    T kin_r = 0.5 * (ur[1] * v1r + ur[2] * v2r + ur[3] * v3r);
+    T mag_l = ul[5] * ul[5] + ul[6] * ul[6] + ul[7] * ul[7];
+    T mag_r = ur[5] * ur[5] + ur[6] * ur[6] + ur[7] * ur[7];
+    T p_ll = (p.gamma - 1) * (ul[4] - kin_l - 0.5 * mag_l - 0.5 * ul[8] * ul[8]);
+    T p_rr = (p.gamma - 1) * (ur[4] - kin_r - 0.5 * mag_r - 0.5 * ur[8] * ur[8]);
+    T pt_l = p_ll + 0.5 * mag_l, pt_r = p_rr + 0.5 * mag_r;
+    T sl = sqrt(rho_ll), sr = sqrt(rho_rr);
+    T inv_add = 1.0 / (sl + sr), inv_prod = 1.0 / (sl * sr);
+    T rl = sl * inv_add, rr = sr * inv_add;
+    T v1 = v1l * rl + v1r * rr, v2 = v2l * rl + v2r * rr, v3 = v3l * rl + v3r * rr;
+    T B1 = ul[5] * rr + ur[5] * rl, B2 = ul[6] * rr + ur[6] * rl, B3 = ul[7] * rr + ur[7] * rl;
+    T H_ll = (ul[4] + pt_l) / rho_ll, H_rr = (ur[4] + pt_r) / rho_rr;
+    T H = H_ll * rl + H_rr * rr;
+    T X = 0.5 * (sq(ul[5] - ur[5]) + sq(ul[6] - ur[6]) + sq(ul[7] - ur[7])) * inv_add * inv_add;
+    T b_square = (B1 * B1 + B2 * B2 + B3 * B3) * inv_prod;
+    T a_square = (2.0 - p.gamma) * X + (p.gamma - 1.0) * (H - 0.5 * (v1 * v1 + v2 * v2 + v3 * v3) - b_square);
+    T Bo = (o == 1) ? B1 : (o == 2 ? B2 : B3);
+    T c_a = Bo * Bo * inv_prod;
+    T a_star = sqrt(sq(a_square + b_square) - 4.0 * a_square * c_a);
+    c_f = sqrt(0.5 * (a_square + b_square + a_star));
+    vel_out = (o == 1) ? v1 : (o == 2 ? v2 : v3);
+  }
+  static void noncons_powell(const T* ul, const T* ur, int o, const EqParams&, T* f) {
+    T rho_ll = ul[0];
+    T v1 = ul[1] / rho_ll, v2 = ul[2] / rho_ll, v3 = ul[3] / rho_ll;
+    T B1 = ul[5], B2 = ul[6], B3 = ul[7], psi_ll = ul[8];
+    T vdotB = v1 * B1 + v2 * B2 + v3 * B3;
+    T Bo_rr = ur[4 + o], psi_rr = ur[8];
+    T vo = (o == 1) ? v1 : (o == 2 ? v2 : v3);
+    f[0] = 0;
+    f[1] = B1 * Bo_rr; f[2] = B2 * Bo_rr; f[3] = B3 * Bo_rr;
+    f[4] = vdotB * Bo_rr + vo * psi_ll * psi_rr;
+    f[5] = v1 * Bo_rr; f[6] = v2 * Bo_rr; f[7] = v3 * Bo_rr;
+    f[8] = vo * psi_rr;
+  }
+  static bool two_point(int kind, const T* ul, const T* ur, int o, const EqParams& p, T* f) {
+    switch (kind) {
+      case FLUX_CENTRAL: {
+        T fl[9], fr[9];
+        flux(ul, o, p, fl); flux(ur, o, p, fr);
+        for (int v = 0; v < 9; ++v) f[v] = 0.5 * (fl[v] + fr[v]);
+        return true;
+      }
+      case FLUX_LAX_FRIEDRICHS:
+      case FLUX_LAX_FRIEDRICHS_NAIVE: {
+        T fl[9], fr[9];
+        flux(ul, o, p, fl); flux(ur, o, p, fr);
+        T vl = fabs(ul[o] / ul[0]), vr = fabs(ur[o] / ur[0]);
+        T cl = fast_wavespeed(ul, o, p), cr = fast_wavespeed(ur, o, p);
+        T lam = (kind == FLUX_LAX_FRIEDRICHS_NAIVE) ? std::max(vl, vr) + std::max(cl, cr)
+                                                    : std::max(vl + cl, vr + cr);
+        for (int v = 0; v < 9; ++v) f[v] = 0.5 * (fl[v] + fr[v]) + (-0.5 * lam * (ur[v] - ul[v]));
+        return true;
+      }
+      case FLUX_HLLE: {
+        T vl = ul[o] / ul[0], vr = ur[o] / ur[0];
+        T cl = fast_wavespeed(ul, o, p), cr = fast_wavespeed(ur, o, p);
+        T vroe, croe;
+        fast_wavespeed_roe(ul, ur, o, p, vroe, croe);
+        T lmin = std::min(vl - cl, vroe - croe), lmax = std::max(vr + cr, vroe + croe);
+        if (lmin >= 0 && lmax >= 0) { flux(ul, o, p, f); return true; }
+        if (lmax <= 0 && lmin <= 0) { flux(ur, o, p, f); return true; }
+        T fl[9], fr[9];
+        flux(ul, o, p, fl); flux(ur, o, p, fr);
+        T inv = 1.0 / (lmax - lmin);
+        T fac_ll = lmax * inv, fac_rr = lmin * inv, fac_d = lmin * lmax * inv;
+        for (int v = 0; v < 9; ++v) f[v] = fac_ll * fl[v] - fac_rr * fr[v] + fac_d * (ur[v] - ul[v]);
+        return true;
+      }
+      case FLUX_HINDENLANG_GASSNER: {
+        T ql[9], qr[9];
+        cons2prim(ul, p, ql); cons2prim(ur, p, qr);
+        T rho_ll = ql[0], v1l = ql[1], v2l = ql[2], v3l = ql[3], p_ll = ql[4], B1l = ql[5], B2l = ql[6], B3l = ql[7], psl = ql[8];
+        T rho_rr = qr[0], v1r = qr[1], v2r = qr[2], v3r = qr[3], p_rr = qr[4], B1r = qr[5], B2r = qr[6], B3r = qr[7], psr = qr[8];
+        T rho_mean = ln_mean(rho_ll, rho_rr);
+        T inv_rho_p_mean = p_ll * p_rr * inv_ln_mean(rho_ll * p_rr, rho_rr * p_ll);
+        T v1a = 0.5 * (v1l + v1r), v2a = 0.5 * (v2l + v2r), v3a = 0.5 * (v3l + v3r);
+        T p_avg = 0.5 * (p_ll + p_rr), psi_avg = 0.5 * (psl + psr);
+        T vsq = 0.5 * (v1l * v1r + v2l * v2r + v3l * v3r);
+        T msq = 0.5 * (B1l * B1r + B2l * B2r + B3l * B3r);
+        const double igm1 = 1.0 / (p.gamma - 1);
+        if (o == 1) {
+          f[0] = rho_mean * v1a;
+          f[1] = f[0] * v1a + p_avg + msq - 0.5 * (B1l * B1r + B1r * B1l);
+          f[2] = f[0] * v2a - 0.5 * (B1l * B2r + B1r * B2l);
+          f[3] = f[0] * v3a - 0.5 * (B1l * B3r + B1r * B3l);
+          f[5] = p.c_h * psi_avg;
+          f[6] = 0.5 * (v1l * B2l - v2l * B1l + v1r * B2r - v2r * B1r);
+          f[7] = 0.5 * (v1l * B3l - v3l * B1l + v1r * B3r - v3r * B1r);
+          f[8] = p.c_h * 0.5 * (B1l + B1r);
+          f[4] = f[0] * (vsq + inv_rho_p_mean * igm1) +
+                 0.5 * (+p_ll * v1r + p_rr * v1l + (v1l * B2l * B2r + v1r * B2r * B2l) +
+                        (v1l * B3l * B3r + v1r * B3r * B3l) - (v2l * B1l * B2r + v2r * B1r * B2l) -
+                        (v3l * B1l * B3r + v3r * B1r * B3l) + p.c_h * (B1l * psr + B1r * psl));
+        } else if (o == 2) {
+          f[0] = rho_mean * v2a;
+          f[1] = f[0] * v1a - 0.5 * (B2l * B1r + B2r * B1l);
+          f[2] = f[0] * v2a + p_avg + msq - 0.5 * (B2l * B2r + B2r * B2l);
+          f[3] = f[0] * v3a - 0.5 * (B2l * B3r + B2r * B3l);
+          f[5] = 0.5 * (v2l * B1l - v1l * B2l + v2r * B1r - v1r * B2r);
+          f[6] = p.c_h * psi_avg;
+          f[7] = 0.5 * (v2l * B3l - v3l * B2l + v2r * B3r - v3r * B2r);
+          f[8] = p.c_h * 0.5 * (B2l + B2r);
+          f[4] = f[0] * (vsq + inv_rho_p_mean * igm1) +
+                 0.5 * (+p_ll * v2r + p_rr * v2l + (v2l * B1l * B1r + v2r * B1r * B1l) +
+                        (v2l * B3l * B3r + v2r * B3r * B3l) - (v1l * B2l * B1r + v1r * B2r * B1l) -
+                        (v3l * B2l * B3r + v3r * B2r * B3l) + p.c_h * (B2l * psr + B2r * psl));
+        } else {
+          f[0] = rho_mean * v3a;
+          f[1] = f[0] * v1a - 0.5 * (B3l * B1r + B3r * B1l);
+          f[2] = f[0] * v2a - 0.5 * (B3l * B2r + B3r * B2l);
+          f[3] = f[0] * v3a + p_avg + msq - 0.5 * (B3l * B3r + B3r * B3l);
+          f[5] = 0.5 * (v3l * B1l - v1l * B3l + v3r * B1r - v1r * B3r);
+          f[6] = 0.5 * (v3l * B2l - v2l * B3l + v3r * B2r - v2r * B3r);
+          f[7] = p.c_h * psi_avg;
+          f[8] = p.c_h * 0.5 * (B3l + B3r);
+          f[4] = f[0] * (vsq + inv_rho_p_mean * igm1) +
+                 0.5 * (+p_ll * v3r + p_rr * v3l + (v3l * B1l * B1r + v3r * B1r * B1l) +
+                        (v3l * B2l * B2r + v3r * B2r * B2l) - (v1l * B3l * B1r + v1r * B3r * B1l) -
+                        (v2l * B3l * B2r + v2r * B3r * B2l) + p.c_h * (B3l * psr + B3r * psl));
+        }
+        return true;
+      }
+      default: return false;
+    }
+  }
+};
+
+// ---------------------------------------------------------------------------------------------
+// Initial conditions / source terms (enumerated), Trixi semantics: ic(x, t, equations) -> cons vars
+// ---------------------------------------------------------------------------------------------
+inline void euler_prim2cons(const double* q, const EqParams& p, double* u) {
+  int nd = p.ndim;
+  double ke = 0;
+  u[0] = q[0];
+  for (int d = 0; d < nd; ++d) { u[1 + d] = q[0] * q[1 + d]; ke += u[1 + d] * q[1 + d]; }
+  u[nd + 1] = q[nd + 1] / (p.gamma - 1) + 0.5 * ke;
+}
+
+inline void initial_condition(int ic, const double* x, double t, const EqParams& p, double* u) {
+  const int nd = p.ndim;
+  if (p.kind == EQ_ADVECTION) {
+    if (ic == IC_CONSTANT) { u[0] = 2.0; return; }
+    // initial_condition_convergence_test: c + A sin(omega * sum(x - a t)), c=1, A=0.5, L=2
+    double s = 0;
+    for (int d = 0; d < nd; ++d) s += x[d] - p.advection_velocity[d] * t;
+    const double c = 1.0, A = 0.5, L = 2, f = 1 / L, omega = 2 * M_PI * f;
+    u[0] = c + A * std::sin(omega * s);
+    return;
+  }
+  if (p.kind == EQ_EULER) {
+    if (ic == IC_CONSTANT) {
+      double q[5] = {1.0, 0.1, -0.2, 0.7, 10.0};
+      if (nd < 3) q[nd + 1] = 10.0;
+      euler_prim2cons(q, p, u);
+      return;
+    }
+    if (ic == IC_CONVERGENCE_TEST) {
+      const double c = 2, A = 0.1, L = 2, f = 1 / L, omega = 2 * M_PI * f;
+      double s = -t;
+      for (int d = 0; d < nd; ++d) s += x[d];
+      double ini = c + A * std::sin(omega * s);
+      u[0] = ini;
+      for (int d = 0; d < nd; ++d) u[1 + d] = ini;
+      u[nd + 1] = ini * ini;
+      return;
+    }
+    if (ic == IC_DENSITY_WAVE) {
+      // smooth synthetic state: rho = 1 + 0.5 sin(pi (x+y+z - t*(v1+v2+v3))), v = (0.1,0.2,0.3), p = 20
+      const double v[3] = {0.1, 0.2, 0.3};
+      double s = 0;
+      for (int d = 0; d < nd; ++d) s += x[d] - v[d] * t;
+      double q[5];
+      q[0] = 1 + 0.5 * std::sin(M_PI * s);
+      for (int d = 0; d < nd; ++d) q[1 + d] = v[d];
+      q[nd + 1] = 20.0;
+      euler_prim2cons(q, p, u);
+      return;
+    }
+    // weak blast wave (Hennemann & Gassner 2020, Sec. 6.3)
+    double r2 = 0;
+    for (int d = 0; d < nd; ++d) r2 += x[d] * x[d];
+    double r = std::sqrt(r2);
+    bool out = r > 0.5;
+    double q[5];
+    q[0] = out ? 1.0 : 1.1691;
+    if (nd == 1) {
+      double cos_phi = x[0] > 0 ? 1.0 : -1.0;
+      q[1] = out ? 0.0 : 0.1882 * cos_phi;
+    } else if (nd == 2) {
+      double phi = std::atan2(x[1], x[0]);
+      q[1] = out ? 0.0 : 0.1882 * std::cos(phi);
+      q[2] = out ? 0.0 : 0.1882 * std::sin(phi);
+    } else {
+      double phi = std::atan2(x[1], x[0]);
+      double theta = (r == 0.0) ? 0.0 : std::acos(x[2] / r);
+      q[1] = out ? 0.0 : 0.1882 * std::cos(phi) * std::sin(theta);
+      q[2] = out ? 0.0 : 0.1882 * std::sin(phi) * std::sin(theta);
+      q[3] = out ? 0.0 : 0.1882 * std::cos(theta);
+    }
+    q[nd + 1] = out ? 1.0 : 1.245;
+    euler_prim2cons(q, p, u);
+    return;
+  }
+  // GLM-MHD 3D
+  if (ic == IC_CONSTANT) {
+    double q[9] = {1.0, 0.1, -0.2, 0.3, 1.5, 0.4, -0.3, 0.2, 0.05};
+    u[0] = q[0]; u[1] = q[0] * q[1]; u[2] = q[0] * q[2]; u[3] = q[0] * q[3];
+    u[5] = q[5]; u[6] = q[6]; u[7] = q[7]; u[8] = q[8];
+    u[4] = q[4] / (p.gamma - 1) + 0.5 * (u[1] * q[1] + u[2] * q[2] + u[3] * q[3]) +
+           0.5 * (q[5] * q[5] + q[6] * q[6] + q[7] * q[7]) + 0.5 * q[8] * q[8];
+    return;
+  }
+  if (ic == IC_WEAK_BLAST_WAVE) {
+    double r = std::sqrt(x[0] * x[0] + x[1] * x[1] + x[2] * x[2]);
+    double phi = std::atan2(x[1], x[0]);
+    double theta = (r == 0.0) ? 0.0 : std::acos(x[2] / r);
+    bool out = r > 0.5;
+    double rho = out ? 1.0 : 1.1691;
+    double v1 = out ? 0.0 : 0.1882 * std::cos(phi) * std::sin(theta);
+    double v2 = out ? 0.0 : 0.1882 * std::sin(phi) * std::sin(theta);
+    double v3 = out ? 0.0 : 0.1882 * std::cos(theta);
+    double pr = out ? 1.0 : 1.245;
+    double B[3] = {1.0, 1.0, 1.0};
+    u[0] = rho; u[1] = rho * v1; u[2] = rho * v2; u[3] = rho * v3;
+    u[5] = B[0]; u[6] = B[1]; u[7] = B[2]; u[8] = 0.0;
+    u[4] = pr / (p.gamma - 1) + 0.5 * (u[1] * v1 + u[2] * v2 + u[3] * v3) + 0.5 * 3.0;
+    return;
+  }
+  {
+    // initial_condition_convergence_test (Alfven wave), domain [-1,1]^3, gamma = 5/3
+    const double omega = 2.0 * M_PI, r = 2.0, e = 0.2;
+    double nx = 1 / std::sqrt(r * r + 1.0), ny = r / std::sqrt(r * r + 1.0);
+    double sqr = 1.0, Va = omega / (ny * sqr);
+    double phi_alv = omega / ny * (nx * (x[0] - 0.5 * r) + ny * (x[1] - 0.5 * r)) - Va * t;
+    double rho = 1.0;
+    double v1 = -e * ny * std::cos(phi_alv) / rho;
+    double v2 = e * nx * std::cos(phi_alv) / rho;
+    double v3 = e * std::sin(phi_alv) / rho;
+    double pr = 1.0;
+    double B1 = nx - rho * v1 * sqr, B2 = ny - rho * v2 * sqr, B3 = -rho * v3 * sqr, psi = 0.0;
+    u[0] = rho; u[1] = rho * v1; u[2] = rho * v2; u[3] = rho * v3;
+    u[5] = B1; u[6] = B2; u[7] = B3; u[8] = psi;
+    u[4] = pr / (p.gamma - 1) + 0.5 * (u[1] * v1 + u[2] * v2 + u[3] * v3) + 0.5 * (B1 * B1 + B2 * B2 + B3 * B3) +
+           0.5 * psi * psi;
+  }
+}
+
+// du += S(u, x, t). Euler `source_terms_convergence_test` for rho = rho_v_i = ini, rho_e = ini^2
+// (manufactured solution; written in a dimension-generic closed form algebraically equal to Trixi's).
+inline void source_terms(int src, const double* /*u*/, const double* x, double t, const EqParams& p, double* s) {
+  const int nd = p.ndim;
+  for (int v = 0; v < p.nvars; ++v) s[v] = 0;
+  if (src != SRC_CONVERGENCE_TEST || p.kind != EQ_EULER) return;
+  const double c = 2, A = 0.1, L = 2, f = 1 / L, omega = 2 * M_PI * f, g = p.gamma;
+  double arg = -t;
+  for (int d = 0; d < nd; ++d) arg += x[d];
+  double si = std::sin(omega * arg), co = std::cos(omega * arg);
+  double q = c + A * si;
+  double tmp1 = co * A * omega;
+  double mom = tmp1 * ((nd - 1) + (g - 1) * (2 * q - 0.5 * nd));
+  s[0] = (nd - 1) * tmp1;
+  for (int d = 0; d < nd; ++d) s[1 + d] = mom;
+  s[nd + 1] = tmp1 * (2 * q * (nd - 1) + nd * (g - 1) * (2 * q - 0.5 * nd));
+}
+
+}  // namespace orc
