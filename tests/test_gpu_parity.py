@@ -1,0 +1,206 @@
+"""GPU parity tests (-m gpu): libtrixib200 (through the C ABI) vs the CPU oracle on the same mesh, equations
+and initial condition. Structure follows the reference's per-stage differential tests
+(reference test/tree_dgsem_3d/euler_ec.jl:53-121): u0, then every rhs! stage's output array, then du.
+Tolerance: du within 1e-12 relative to max|du_ref| (BASELINE.json north_star); connectivity exact."""
+import numpy as np
+import pytest
+
+import cases
+from cases import CASES, make_oracle, make_semi, rel_max_err, nan_rule_equal
+
+pytestmark = pytest.mark.gpu
+TOL = 1e-12
+
+STAGES = ["calc_volume_integral", "prolong2interfaces", "calc_interface_flux", "prolong2boundaries",
+          "calc_boundary_flux", "prolong2mortars", "calc_mortar_flux", "calc_surface_integral", "apply_jacobian",
+          "calc_sources"]
+
+
+def _torch():
+    import torch
+    return torch
+
+
+def _to_dev(semi, a):
+    return _torch().from_numpy(np.ascontiguousarray(a)).to(semi.device)
+
+
+@pytest.mark.parametrize("name", sorted(CASES))
+def test_u0_matches_oracle(name):
+    c = CASES[name]
+    o, semi = make_oracle(c), make_semi(c, staged_only=True)
+    u_ref = o.compute_coefficients(0.3)
+    # host path of the shim (Trixi compute_coefficients + upload) is bit-exact for the polynomial parts and
+    # within libm rounding for the trigonometric ICs
+    u_host = semi.compute_coefficients(0.3)
+    assert rel_max_err(u_host, u_ref) <= 1e-14
+    # device-side enumerated IC (benchmark path)
+    u_dev = semi.compute_coefficients_gpu(0.3, on_device=True).cpu().numpy()
+    assert rel_max_err(u_dev, u_ref) <= 1e-14
+
+
+@pytest.mark.parametrize("name", sorted(CASES))
+def test_stages_match_oracle(name):
+    """Every stage in the reference's order, comparing the array that stage writes."""
+    c = CASES[name]
+    o, semi = make_oracle(c), make_semi(c, staged_only=True)
+    assert not semi.fused
+    t = 0.1
+    u = o.compute_coefficients(0.0)
+    du_ref = o.new_u()
+    u_d, du_d = _to_dev(semi, u), semi.new_vector().zero_()
+    mortar_names = {3: ["mortars.u_upper_left", "mortars.u_upper_right", "mortars.u_lower_left",
+                        "mortars.u_lower_right"], 2: ["mortars.u_upper", "mortars.u_lower"], 1: []}[c["ndim"]]
+    o.stage("reset_du", du_ref, u, t)
+    semi.stage("reset_du", du_d, u_d, t)
+    for st in STAGES:
+        o.stage(st, du_ref, u, t)
+        semi.stage(st, du_d, u_d, t)
+        if st in ("calc_volume_integral", "calc_surface_integral", "apply_jacobian", "calc_sources"):
+            assert rel_max_err(du_d.cpu().numpy(), du_ref) <= TOL, st
+        elif st == "prolong2interfaces":
+            assert np.array_equal(semi.cache("interfaces.u"), o.f64("interfaces.u")), st   # pure gather: exact
+        elif st in ("calc_interface_flux", "calc_boundary_flux", "calc_mortar_flux"):
+            assert rel_max_err(semi.cache("surface_flux_values"), o.f64("surface_flux_values")) <= TOL, st
+        elif st == "prolong2boundaries":
+            assert nan_rule_equal(semi.cache("boundaries.u"), o.f64("boundaries.u")), st
+        elif st == "prolong2mortars":
+            for mn in mortar_names:
+                assert nan_rule_equal(semi.cache(mn), o.f64(mn), tol=1e-14), mn
+    if c["vi"] == "shock_capturing_hg":
+        assert np.abs(semi.cache("alpha") - o.f64("alpha")).max() <= 1e-12
+
+
+@pytest.mark.parametrize("staged_only", [True, False], ids=["staged", "fused"])
+@pytest.mark.parametrize("name", sorted(CASES))
+def test_rhs_matches_oracle(name, staged_only):
+    """Whole rhs!: du within 1e-12 (relative max-norm) of the CPU reference after one call."""
+    c = CASES[name]
+    o, semi = make_oracle(c), make_semi(c, staged_only=staged_only)
+    if not staged_only and not semi.fused:
+        pytest.skip("fused path covers polydeg 3 in 2D/3D; this case runs the staged kernels")
+    for t0 in (0.0, 0.37):
+        u = o.compute_coefficients(t0)
+        du_ref = o.rhs(u, t0)
+        u_d, du_d = _to_dev(semi, u), semi.new_vector().fill_(float("nan"))
+        semi.rhs(du_d, u_d, t0)
+        err = rel_max_err(du_d.cpu().numpy(), du_ref)
+        assert np.isfinite(du_d.cpu().numpy()).all()
+        assert err <= TOL, (name, err)
+
+
+@pytest.mark.parametrize("name", ["c5_euler_ec_3d", "c2_euler_ec_2d", "c3_euler_sc_3d", "advection_basic_3d",
+                                  "c4_mhd_alfven_mortar_3d"])
+def test_fused_equals_staged_on_random_state(name):
+    """Non-smooth states exercise both ln_mean branches; fused and staged kernels must agree to round-off and
+    with the oracle."""
+    c = CASES[name]
+    o, fused, staged = make_oracle(c), make_semi(c), make_semi(c, staged_only=True)
+    assert fused.fused and not staged.fused
+    rng = np.random.default_rng(7)
+    u = o.compute_coefficients(0.0)
+    nv = o.nvars
+    pert = 1.0 + 0.2 * rng.uniform(-1, 1, size=u.size // nv)
+    uu = u.reshape(-1, nv).copy()
+    uu[:, 0] *= pert                      # density (or the scalar): +-20 % node-to-node jumps
+    if nv > 1:
+        uu[:, -1 if c["equations"] == "euler" else 4] *= 1.0 + 0.2 * rng.uniform(0, 1, size=pert.size)
+    u = uu.ravel()
+    du_ref = o.rhs(u, 0.0)
+    outs = []
+    for semi in (fused, staged):
+        u_d, du_d = _to_dev(semi, u), semi.new_vector()
+        semi.rhs(du_d, u_d, 0.0)
+        outs.append(du_d.cpu().numpy())
+        assert rel_max_err(outs[-1], du_ref) <= TOL
+    assert rel_max_err(outs[0], outs[1]) <= TOL
+
+
+@pytest.mark.parametrize("name", sorted(CASES))
+def test_max_dt_matches_oracle(name):
+    c = CASES[name]
+    o, semi = make_oracle(c), make_semi(c)
+    u = o.compute_coefficients(0.0)
+    ref = o.max_dt(u)
+    got = semi.max_dt(_to_dev(semi, u), 0.0)
+    assert abs(got - ref) <= 1e-13 * abs(ref)
+
+
+def test_full_run_error_norms_c1():
+    """examples/advection_basic_1d.jl end to end (level 4, p=3, LLF, CFL 1.6, CK2N54, t in [0,1]): analysis
+    L2/Linf within 1e-10 of the CPU reference; the reference values are also Trixi's published regression
+    numbers (tests/golden/trixi_regression_norms.json)."""
+    import trixib200 as T
+    c = CASES["c1_advection_1d"]
+    o, semi = make_oracle(c), make_semi(c)
+    u_ref, steps_ref = o.solve(o.compute_coefficients(0.0), 0.0, 1.0, cfl=1.6)
+    l2_ref, linf_ref = o.error_norms(u_ref, 1.0)
+    ode = T.semidiscretizeGPU(semi, (0.0, 1.0))
+    ana = T.AnalysisCallback(semi, interval=100)
+    sol = T.solve(ode, T.CarpenterKennedy2N54(williamson_condition=False), dt=1.0,
+                  callback=T.CallbackSet(ana, T.StepsizeCallback(cfl=1.6)))
+    assert sol.nsteps == steps_ref
+    t, l2, linf = ana.history[-1]
+    assert abs(l2[0] - l2_ref[0]) <= 1e-10 and abs(linf[0] - linf_ref[0]) <= 1e-10
+    assert abs(l2[0] - 6.0388296447998465e-6) <= 1e-10 and abs(linf[0] - 3.217887726258972e-5) <= 1e-10
+
+
+@pytest.mark.parametrize("name,tend,cfl", [("c2_euler_ec_2d", 0.1, 1.0), ("c5_euler_ec_3d", 0.1, 1.3),
+                                           ("c3_euler_sc_3d", 0.05, 1.4), ("c4_mhd_alfven_mortar_3d", 0.05, 1.0)])
+def test_full_run_error_norms(name, tend, cfl):
+    import trixib200 as T
+    c = CASES[name]
+    o, semi = make_oracle(c), make_semi(c)
+    u_ref, steps_ref = o.solve(o.compute_coefficients(0.0), 0.0, tend, cfl=cfl)
+    l2_ref, linf_ref = o.error_norms(u_ref, tend)
+    ode = T.semidiscretizeGPU(semi, (0.0, tend))
+    ana = T.AnalysisCallback(semi)
+    sol = T.solve(ode, T.CarpenterKennedy2N54(), callback=T.CallbackSet(ana, T.StepsizeCallback(cfl=cfl)))
+    assert sol.nsteps == steps_ref
+    _, l2, linf = ana.history[-1]
+    assert np.abs(l2 - l2_ref).max() <= 1e-10 and np.abs(linf - linf_ref).max() <= 1e-10
+    assert rel_max_err(sol.u[-1].cpu().numpy(), u_ref) <= 1e-10
+
+
+def test_large_mesh_properties():
+    """Size-independent properties at a size the oracle would not finish in seconds (3D Euler EC, level 5,
+    2.1 M DOF): free-stream preservation, discrete conservation and entropy conservation of the EC scheme."""
+    c = dict(CASES["c5_euler_ec_3d"], level=5)
+    semi = make_semi(c)
+    torch = _torch()
+    E, nn, nv = semi.nelements, 64, 5
+    # free stream: constant state -> du == 0 to round-off
+    u = torch.tensor([1.0, 0.1, -0.2, 0.7, 25.0], dtype=torch.float64, device=semi.device).repeat(E * nn)
+    du = semi.new_vector()
+    semi.rhs(du, u, 0.0)
+    assert du.abs().max().item() <= 1e-11
+    # conservation: sum_e J_e^3 sum_n w_n du = 0 for every variable
+    ode_u = semi.compute_coefficients_gpu(0.0, on_device=True)
+    semi.rhs(du, ode_u, 0.0)
+    w = torch.tensor(semi.solver.basis.weights, dtype=torch.float64, device=semi.device)
+    w3 = (w[:, None, None] * w[None, :, None] * w[None, None, :]).reshape(1, 64, 1)
+    jac = (1.0 / torch.tensor(semi.cache_cpu.elements.inverse_jacobian, device=semi.device)) ** 3
+    integ = (du.view(E, nn, nv) * w3 * jac.view(E, 1, 1)).sum(dim=(0, 1))
+    scale = (du.view(E, nn, nv).abs() * w3 * jac.view(E, 1, 1)).sum(dim=(0, 1))
+    assert (integ.abs() / scale).max().item() <= 1e-12
+    # entropy conservation: sum w(u) . du = 0 (flux_ranocha volume + surface)
+    U = ode_u.view(E, nn, nv)
+    rho, e = U[..., 0], U[..., 4]
+    v = U[..., 1:4] / rho[..., None]
+    p = 0.4 * (e - 0.5 * rho * (v * v).sum(-1))
+    s = torch.log(p) - 1.4 * torch.log(rho)
+    wv = torch.stack([(1.4 - s) / 0.4 - 0.5 * rho / p * (v * v).sum(-1), rho / p * v[..., 0], rho / p * v[..., 1],
+                      rho / p * v[..., 2], -rho / p], dim=-1)
+    dS = ((wv * du.view(E, nn, nv)).sum(-1, keepdim=True) * w3 * jac.view(E, 1, 1)).sum().item()
+    dS_scale = ((wv * du.view(E, nn, nv)).abs().sum(-1, keepdim=True) * w3 * jac.view(E, 1, 1)).sum().item()
+    assert abs(dS) / dS_scale <= 1e-12
+
+
+def test_unsupported_combinations_raise():
+    import trixib200 as T
+    c = dict(CASES["c5_euler_ec_3d"], volume_flux="flux_lax_friedrichs")   # not a symmetric two-point flux
+    with pytest.raises(T.TrixiB200Error):
+        make_semi(c)
+    c = dict(CASES["advection_basic_3d"], surface_flux="flux_ranocha")
+    with pytest.raises(T.TrixiB200Error):
+        make_semi(c)

@@ -1,0 +1,525 @@
+// Device functors for the enumerated physics surface (equations x fluxes x ICs x sources).
+// The reference receives these as Julia callables from Trixi.jl and inlines them into its kernels
+// (reference src/solvers/dg_3d_kernel.jl:93-95,226-234,387-395,1166,1190-1191,1327-1343,1836;
+//  src/callbacks_step/stepsize_dg_3d.jl:34). A C ABI cannot take closures, so the library ships these.
+#pragma once
+#include <cuda_runtime.h>
+#include <math.h>
+#include "../../include/trixib200.h"
+
+#define TB_HD __host__ __device__ __forceinline__
+#define TB_D __device__ __forceinline__
+
+namespace tb {
+
+struct EqPrm {
+  double gamma;
+  double a[3];
+  double c_h;
+};
+
+TB_D double sq(double x) { return x * x; }
+
+// Trixi ln_mean / inv_ln_mean (Ismail-Roe / Ranocha)
+TB_D double ln_mean(double x, double y) {
+  double f2 = (x * (x - 2 * y) + y * y) / (x * (x + 2 * y) + y * y);
+  if (f2 < 1.0e-4) return (x + y) / (2 + f2 * (2.0 / 3 + f2 * (2.0 / 5 + f2 * (2.0 / 7))));
+  return (y - x) / log(y / x);
+}
+TB_D double inv_ln_mean(double x, double y) {
+  double f2 = (x * (x - 2 * y) + y * y) / (x * (x + 2 * y) + y * y);
+  if (f2 < 1.0e-4) return (2 + f2 * (2.0 / 3 + f2 * (2.0 / 5 + f2 * (2.0 / 7)))) / (x + y);
+  return log(y / x) / (y - x);
+}
+
+// ------------------------------------------------------------------------------------ advection
+template <int ND> struct EqAdvection {
+  static constexpr int NV = 1, NDIM = ND, KIND = TRIXIB200_EQ_ADVECTION;
+  static constexpr bool HAS_NONCONS = false;
+  static bool supports_flux(int k) {
+    return k == TRIXIB200_FLUX_CENTRAL || k == TRIXIB200_FLUX_LAX_FRIEDRICHS || k == TRIXIB200_FLUX_LAX_FRIEDRICHS_NAIVE;
+  }
+  TB_D static void flux(const double* u, int o, const EqPrm& p, double* f) { f[0] = p.a[o - 1] * u[0]; }
+  TB_D static void two_point(int kind, const double* ul, const double* ur, int o, const EqPrm& p, double* f) {
+    double a = p.a[o - 1];
+    double c = 0.5 * (a * ul[0] + a * ur[0]);
+    if (kind == TRIXIB200_FLUX_CENTRAL) f[0] = c;
+    else f[0] = c - 0.5 * fabs(a) * (ur[0] - ul[0]);
+  }
+  TB_D static void noncons(const double*, const double*, int, const EqPrm&, double* g) { g[0] = 0; }
+  // "q" = per-node working variables of the fused kernel (advection: q == u)
+  TB_D static void to_q(const double* u, const EqPrm&, double* q) { q[0] = u[0]; }
+  TB_D static void two_point_q(int kind, const double* ql, const double* qr, int o, const EqPrm& p, double* f) {
+    two_point(kind, ql, qr, o, p, f);
+  }
+  TB_D static void noncons_q(const double*, const double*, int, const EqPrm&, double* g) { g[0] = 0; }
+  TB_D static void max_abs_speeds(const double*, const EqPrm& p, double* lam) {
+#pragma unroll
+    for (int d = 0; d < ND; ++d) lam[d] = fabs(p.a[d]);
+  }
+  TB_D static double indicator_var(int, const double* u, const EqPrm&) { return u[0]; }
+  TB_D static void initial_condition(int ic, const double* x, double t, const EqPrm& p, double* u) {
+    if (ic == TRIXIB200_IC_CONSTANT) { u[0] = 2.0; return; }
+    double s = 0;
+#pragma unroll
+    for (int d = 0; d < ND; ++d) s += x[d] - p.a[d] * t;
+    const double c = 1.0, A = 0.5, L = 2, f = 1 / L, omega = 2 * M_PI * f;
+    u[0] = c + A * sin(omega * s);
+  }
+  TB_D static void source(int, const double*, const double*, double, const EqPrm&, double* s) { s[0] = 0; }
+};
+
+// ------------------------------------------------------------------------------------ compressible Euler
+template <int ND> struct EqEuler {
+  static constexpr int NV = ND + 2, NDIM = ND, KIND = TRIXIB200_EQ_EULER;
+  static constexpr bool HAS_NONCONS = false;
+  static bool supports_flux(int k) { return k >= TRIXIB200_FLUX_CENTRAL && k <= TRIXIB200_FLUX_SHIMA_ETAL; }
+
+  // component 1+d of a state selected by the (possibly per-lane) orientation without dynamic indexing
+  TB_D static double osel(const double* q, int o) {
+    double r = q[1];
+    if (ND > 1 && o == 2) r = q[2];
+    if (ND > 2 && o == 3) r = q[ND];
+    return r;
+  }
+  TB_D static void cons2prim(const double* u, const EqPrm& p, double* q) {
+    double rho = u[0], ke = 0;
+#pragma unroll
+    for (int d = 0; d < ND; ++d) { q[1 + d] = u[1 + d] / rho; ke += u[1 + d] * q[1 + d]; }
+    q[0] = rho;
+    q[ND + 1] = (p.gamma - 1) * (u[ND + 1] - 0.5 * ke);
+  }
+  TB_D static void prim2cons(const double* q, const EqPrm& p, double* u) {
+    double ke = 0;
+    u[0] = q[0];
+#pragma unroll
+    for (int d = 0; d < ND; ++d) { u[1 + d] = q[0] * q[1 + d]; ke += u[1 + d] * q[1 + d]; }
+    u[ND + 1] = q[ND + 1] / (p.gamma - 1) + 0.5 * ke;
+  }
+  TB_D static void flux(const double* u, int o, const EqPrm& p, double* f) {
+    double q[NV];
+    cons2prim(u, p, q);
+    double uo = osel(u, o), v = osel(q, o), pr = q[ND + 1];
+    f[0] = uo;
+#pragma unroll
+    for (int d = 0; d < ND; ++d) f[1 + d] = uo * q[1 + d] + ((d + 1 == o) ? pr : 0.0);
+    f[ND + 1] = (u[ND + 1] + pr) * v;
+  }
+  // entropy-conservative / kinetic-energy-preserving fluxes written on primitive variables (rho, v, p)
+  TB_D static void ec_flux_q(int kind, const double* ql, const double* qr, int o, const EqPrm& p, double* f) {
+    double p_ll = ql[ND + 1], p_rr = qr[ND + 1];
+    double vavg[ND], vsq = 0, vo_avg = 0;
+#pragma unroll
+    for (int d = 0; d < ND; ++d) {
+      vavg[d] = 0.5 * (ql[1 + d] + qr[1 + d]);
+      vsq += ql[1 + d] * qr[1 + d];
+      if (d + 1 == o) vo_avg = vavg[d];
+    }
+    double p_avg = 0.5 * (p_ll + p_rr);
+    double velocity_square_avg = 0.5 * vsq;
+    double pv = 0.5 * (p_ll * osel(qr, o) + p_rr * osel(ql, o));
+    if (kind == TRIXIB200_FLUX_RANOCHA) {
+      double rho_mean = ln_mean(ql[0], qr[0]);
+      double inv_rho_p_mean = p_ll * p_rr * inv_ln_mean(ql[0] * p_rr, qr[0] * p_ll);
+      double f1 = rho_mean * vo_avg;
+      f[0] = f1;
+#pragma unroll
+      for (int d = 0; d < ND; ++d) f[1 + d] = f1 * vavg[d] + ((d + 1 == o) ? p_avg : 0.0);
+      f[ND + 1] = f1 * (velocity_square_avg + inv_rho_p_mean / (p.gamma - 1)) + pv;
+    } else {
+      double rho_avg = 0.5 * (ql[0] + qr[0]);
+      double f1 = rho_avg * vo_avg;
+      f[0] = f1;
+#pragma unroll
+      for (int d = 0; d < ND; ++d) f[1 + d] = f1 * vavg[d] + ((d + 1 == o) ? p_avg : 0.0);
+      f[ND + 1] = p_avg * vo_avg / (p.gamma - 1) + f1 * velocity_square_avg + pv;
+    }
+  }
+  TB_D static void to_q(const double* u, const EqPrm& p, double* q) { cons2prim(u, p, q); }
+  TB_D static void two_point_q(int kind, const double* ql, const double* qr, int o, const EqPrm& p, double* f) {
+    if (kind == TRIXIB200_FLUX_RANOCHA || kind == TRIXIB200_FLUX_SHIMA_ETAL) { ec_flux_q(kind, ql, qr, o, p, f); return; }
+    double ul[NV], ur[NV];
+    prim2cons(ql, p, ul); prim2cons(qr, p, ur);
+    two_point(kind, ul, ur, o, p, f);
+  }
+  TB_D static void noncons_q(const double*, const double*, int, const EqPrm&, double* g) {
+#pragma unroll
+    for (int v = 0; v < NV; ++v) g[v] = 0;
+  }
+  TB_D static void two_point(int kind, const double* ul, const double* ur, int o, const EqPrm& p, double* f) {
+    if (kind == TRIXIB200_FLUX_RANOCHA || kind == TRIXIB200_FLUX_SHIMA_ETAL) {
+      double ql[NV], qr[NV];
+      cons2prim(ul, p, ql); cons2prim(ur, p, qr);
+      ec_flux_q(kind, ql, qr, o, p, f);
+      return;
+    }
+    double fl[NV], fr[NV];
+    flux(ul, o, p, fl); flux(ur, o, p, fr);
+    if (kind == TRIXIB200_FLUX_CENTRAL) {
+#pragma unroll
+      for (int v = 0; v < NV; ++v) f[v] = 0.5 * (fl[v] + fr[v]);
+      return;
+    }
+    double ql[NV], qr[NV];
+    cons2prim(ul, p, ql); cons2prim(ur, p, qr);
+    double cl = sqrt(p.gamma * ql[ND + 1] / ql[0]), cr = sqrt(p.gamma * qr[ND + 1] / qr[0]);
+    if (kind == TRIXIB200_FLUX_LAX_FRIEDRICHS || kind == TRIXIB200_FLUX_LAX_FRIEDRICHS_NAIVE) {
+      double vl = fabs(osel(ql, o)), vr = fabs(osel(qr, o));
+      double lam = (kind == TRIXIB200_FLUX_LAX_FRIEDRICHS_NAIVE) ? fmax(vl, vr) + fmax(cl, cr) : fmax(vl + cl, vr + cr);
+#pragma unroll
+      for (int v = 0; v < NV; ++v) f[v] = 0.5 * (fl[v] + fr[v]) + (-0.5 * lam * (ur[v] - ul[v]));
+      return;
+    }
+    // HLL
+    double lmin, lmax;
+    double vol = osel(ql, o), vor = osel(qr, o);
+    if (kind == TRIXIB200_FLUX_HLL_NAIVE) { lmin = vol - cl; lmax = vor + cr; }
+    else { lmin = fmin(vol - cl, vor - cr); lmax = fmax(vol + cl, vor + cr); }
+    if (lmin >= 0 && lmax >= 0) {
+#pragma unroll
+      for (int v = 0; v < NV; ++v) f[v] = fl[v];
+    } else if (lmax <= 0 && lmin <= 0) {
+#pragma unroll
+      for (int v = 0; v < NV; ++v) f[v] = fr[v];
+    } else {
+      double inv = 1.0 / (lmax - lmin);
+      double fac_ll = lmax * inv, fac_rr = lmin * inv, fac_d = lmin * lmax * inv;
+#pragma unroll
+      for (int v = 0; v < NV; ++v) f[v] = fac_ll * fl[v] - fac_rr * fr[v] + fac_d * (ur[v] - ul[v]);
+    }
+  }
+  TB_D static void noncons(const double*, const double*, int, const EqPrm&, double* g) {
+#pragma unroll
+    for (int v = 0; v < NV; ++v) g[v] = 0;
+  }
+  TB_D static void max_abs_speeds(const double* u, const EqPrm& p, double* lam) {
+    double q[NV];
+    cons2prim(u, p, q);
+    double c = sqrt(p.gamma * q[ND + 1] / q[0]);
+#pragma unroll
+    for (int d = 0; d < ND; ++d) lam[d] = fabs(q[1 + d]) + c;
+  }
+  TB_D static double indicator_var(int kind, const double* u, const EqPrm& p) {
+    double q[NV];
+    cons2prim(u, p, q);
+    return kind == TRIXIB200_IND_DENSITY ? q[0] : (kind == TRIXIB200_IND_PRESSURE ? q[ND + 1] : q[0] * q[ND + 1]);
+  }
+  TB_D static void initial_condition(int ic, const double* x, double t, const EqPrm& p, double* u) {
+    double q[NV];
+    if (ic == TRIXIB200_IC_CONSTANT) {
+      const double q0[5] = {1.0, 0.1, -0.2, 0.7, 10.0};
+#pragma unroll
+      for (int v = 0; v < NV; ++v) q[v] = q0[v];
+      q[ND + 1] = 10.0;
+      prim2cons(q, p, u);
+      return;
+    }
+    if (ic == TRIXIB200_IC_CONVERGENCE_TEST) {
+      const double c = 2, A = 0.1, L = 2, f = 1 / L, omega = 2 * M_PI * f;
+      double s = -t;
+#pragma unroll
+      for (int d = 0; d < ND; ++d) s += x[d];
+      double ini = c + A * sin(omega * s);
+      u[0] = ini;
+#pragma unroll
+      for (int d = 0; d < ND; ++d) u[1 + d] = ini;
+      u[ND + 1] = ini * ini;
+      return;
+    }
+    if (ic == TRIXIB200_IC_DENSITY_WAVE) {
+      const double v[3] = {0.1, 0.2, 0.3};
+      double s = 0;
+#pragma unroll
+      for (int d = 0; d < ND; ++d) s += x[d] - v[d] * t;
+      q[0] = 1 + 0.5 * sin(M_PI * s);
+#pragma unroll
+      for (int d = 0; d < ND; ++d) q[1 + d] = v[d];
+      q[ND + 1] = 20.0;
+      prim2cons(q, p, u);
+      return;
+    }
+    // weak blast wave
+    double r2 = 0;
+#pragma unroll
+    for (int d = 0; d < ND; ++d) r2 += x[d] * x[d];
+    double r = sqrt(r2);
+    bool out = r > 0.5;
+    q[0] = out ? 1.0 : 1.1691;
+    if (ND == 1) {
+      q[1] = out ? 0.0 : 0.1882 * (x[0] > 0 ? 1.0 : -1.0);
+    } else if (ND == 2) {
+      double phi = atan2(x[1], x[0]);
+      q[1] = out ? 0.0 : 0.1882 * cos(phi);
+      q[2] = out ? 0.0 : 0.1882 * sin(phi);
+    } else {
+      double phi = atan2(x[1], x[0]);
+      double theta = (r == 0.0) ? 0.0 : acos(x[ND - 1] / r);
+      q[1] = out ? 0.0 : 0.1882 * cos(phi) * sin(theta);
+      q[2] = out ? 0.0 : 0.1882 * sin(phi) * sin(theta);
+      q[ND] = out ? 0.0 : 0.1882 * cos(theta);
+    }
+    q[ND + 1] = out ? 1.0 : 1.245;
+    prim2cons(q, p, u);
+  }
+  // source_terms_convergence_test for rho = rho_v_i = ini, rho_e = ini^2 (dimension-generic closed form)
+  TB_D static void source(int src, const double*, const double* x, double t, const EqPrm& p, double* s) {
+#pragma unroll
+    for (int v = 0; v < NV; ++v) s[v] = 0;
+    if (src != TRIXIB200_SRC_CONVERGENCE_TEST) return;
+    const double c = 2, A = 0.1, L = 2, f = 1 / L, omega = 2 * M_PI * f, g = p.gamma;
+    double arg = -t;
+#pragma unroll
+    for (int d = 0; d < ND; ++d) arg += x[d];
+    double si = sin(omega * arg), co = cos(omega * arg);
+    double q = c + A * si;
+    double tmp1 = co * A * omega;
+    double mom = tmp1 * ((ND - 1) + (g - 1) * (2 * q - 0.5 * ND));
+    s[0] = (ND - 1) * tmp1;
+#pragma unroll
+    for (int d = 0; d < ND; ++d) s[1 + d] = mom;
+    s[ND + 1] = tmp1 * (2 * q * (ND - 1) + ND * (g - 1) * (2 * q - 0.5 * ND));
+  }
+};
+
+// ------------------------------------------------------------------------------------ ideal GLM-MHD 3D
+struct EqMhd3 {
+  static constexpr int NV = 9, NDIM = 3, KIND = TRIXIB200_EQ_MHD;
+  static constexpr bool HAS_NONCONS = true;
+  static bool supports_flux(int k) {
+    return k == TRIXIB200_FLUX_CENTRAL || k == TRIXIB200_FLUX_LAX_FRIEDRICHS || k == TRIXIB200_FLUX_LAX_FRIEDRICHS_NAIVE ||
+           k == TRIXIB200_FLUX_HINDENLANG_GASSNER || k == TRIXIB200_FLUX_HLLE;
+  }
+  TB_D static void cons2prim(const double* u, const EqPrm& p, double* q) {
+    double rho = u[0];
+    double v1 = u[1] / rho, v2 = u[2] / rho, v3 = u[3] / rho;
+    q[4] = (p.gamma - 1) * (u[4] - 0.5 * (u[1] * v1 + u[2] * v2 + u[3] * v3) -
+                            0.5 * (u[5] * u[5] + u[6] * u[6] + u[7] * u[7]) - 0.5 * u[8] * u[8]);
+    q[0] = rho; q[1] = v1; q[2] = v2; q[3] = v3; q[5] = u[5]; q[6] = u[6]; q[7] = u[7]; q[8] = u[8];
+  }
+  TB_D static void flux(const double* u, int o, const EqPrm& p, double* f) {
+    double rho = u[0], B1 = u[5], B2 = u[6], B3 = u[7], psi = u[8];
+    double v1 = u[1] / rho, v2 = u[2] / rho, v3 = u[3] / rho;
+    double kin_en = 0.5 * (u[1] * v1 + u[2] * v2 + u[3] * v3);
+    double mag_en = 0.5 * (B1 * B1 + B2 * B2 + B3 * B3);
+    double p_over_gm1 = (u[4] - kin_en - mag_en - 0.5 * psi * psi);
+    double pr = (p.gamma - 1) * p_over_gm1;
+    double vdotB = v1 * B1 + v2 * B2 + v3 * B3;
+    double en = kin_en + p.gamma * p_over_gm1 + 2 * mag_en;
+    if (o == 1) {
+      f[0] = u[1]; f[1] = u[1] * v1 + pr + mag_en - B1 * B1; f[2] = u[1] * v2 - B1 * B2; f[3] = u[1] * v3 - B1 * B3;
+      f[4] = en * v1 - B1 * vdotB + p.c_h * psi * B1;
+      f[5] = p.c_h * psi; f[6] = v1 * B2 - v2 * B1; f[7] = v1 * B3 - v3 * B1; f[8] = p.c_h * B1;
+    } else if (o == 2) {
+      f[0] = u[2]; f[1] = u[2] * v1 - B2 * B1; f[2] = u[2] * v2 + pr + mag_en - B2 * B2; f[3] = u[2] * v3 - B2 * B3;
+      f[4] = en * v2 - B2 * vdotB + p.c_h * psi * B2;
+      f[5] = v2 * B1 - v1 * B2; f[6] = p.c_h * psi; f[7] = v2 * B3 - v3 * B2; f[8] = p.c_h * B2;
+    } else {
+      f[0] = u[3]; f[1] = u[3] * v1 - B3 * B1; f[2] = u[3] * v2 - B3 * B2; f[3] = u[3] * v3 + pr + mag_en - B3 * B3;
+      f[4] = en * v3 - B3 * vdotB + p.c_h * psi * B3;
+      f[5] = v3 * B1 - v1 * B3; f[6] = v3 * B2 - v2 * B3; f[7] = p.c_h * psi; f[8] = p.c_h * B3;
+    }
+  }
+  TB_D static double fast_wavespeed(const double* u, int o, const EqPrm& p) {
+    double rho = u[0];
+    double v1 = u[1] / rho, v2 = u[2] / rho, v3 = u[3] / rho;
+    double kin_en = 0.5 * (u[1] * v1 + u[2] * v2 + u[3] * v3);
+    double mag_en = 0.5 * (u[5] * u[5] + u[6] * u[6] + u[7] * u[7]);
+    double pr = (p.gamma - 1) * (u[4] - kin_en - mag_en - 0.5 * u[8] * u[8]);
+    double a_square = p.gamma * pr / rho;
+    double sqrt_rho = sqrt(rho);
+    double b1 = u[5] / sqrt_rho, b2 = u[6] / sqrt_rho, b3 = u[7] / sqrt_rho;
+    double b_square = b1 * b1 + b2 * b2 + b3 * b3;
+    double bo = (o == 1) ? b1 : (o == 2 ? b2 : b3);
+    return sqrt(0.5 * (a_square + b_square) + 0.5 * sqrt(sq(a_square + b_square) - 4.0 * a_square * bo * bo));
+  }
+  TB_D static void fast_wavespeed_roe(const double* ul, const double* ur, int o, const EqPrm& p, double& vel_out, double& c_f) {
+    double rho_ll = ul[0], rho_rr = ur[0];
+    double v1l = ul[1] / rho_ll, v2l = ul[2] / rho_ll, v3l = ul[3] / rho_ll;
+    double v1r = ur[1] / rho_rr, v2r = ur[2] / rho_rr, v3r = ur[3] / rho_rr;
+    double kin_l = 0.5 * (ul[1] * v1l + ul[2] * v2l + ul[3] * v3l);
+    double kin_r = 0.5 * (ur[1] * v1r + ur[2] * v2r + ur[3] * v3r);
+    double mag_l = ul[5] * ul[5] + ul[6] * ul[6] + ul[7] * ul[7];
+    double mag_r = ur[5] * ur[5] + ur[6] * ur[6] + ur[7] * ur[7];
+    double p_ll = (p.gamma - 1) * (ul[4] - kin_l - 0.5 * mag_l - 0.5 * ul[8] * ul[8]);
+    double p_rr = (p.gamma - 1) * (ur[4] - kin_r - 0.5 * mag_r - 0.5 * ur[8] * ur[8]);
+    double pt_l = p_ll + 0.5 * mag_l, pt_r = p_rr + 0.5 * mag_r;
+    double sl = sqrt(rho_ll), sr = sqrt(rho_rr);
+    double inv_add = 1.0 / (sl + sr), inv_prod = 1.0 / (sl * sr);
+    double rl = sl * inv_add, rr = sr * inv_add;
+    double v1 = v1l * rl + v1r * rr, v2 = v2l * rl + v2r * rr, v3 = v3l * rl + v3r * rr;
+    double B1 = ul[5] * rr + ur[5] * rl, B2 = ul[6] * rr + ur[6] * rl, B3 = ul[7] * rr + ur[7] * rl;
+    double H_ll = (ul[4] + pt_l) / rho_ll, H_rr = (ur[4] + pt_r) / rho_rr;
+    double H = H_ll * rl + H_rr * rr;
+    double X = 0.5 * (sq(ul[5] - ur[5]) + sq(ul[6] - ur[6]) + sq(ul[7] - ur[7])) * inv_add * inv_add;
+    double b_square = (B1 * B1 + B2 * B2 + B3 * B3) * inv_prod;
+    double a_square = (2.0 - p.gamma) * X + (p.gamma - 1.0) * (H - 0.5 * (v1 * v1 + v2 * v2 + v3 * v3) - b_square);
+    double Bo = (o == 1) ? B1 : (o == 2 ? B2 : B3);
+    double c_a = Bo * Bo * inv_prod;
+    double a_star = sqrt(sq(a_square + b_square) - 4.0 * a_square * c_a);
+    c_f = sqrt(0.5 * (a_square + b_square + a_star));
+    vel_out = (o == 1) ? v1 : (o == 2 ? v2 : v3);
+  }
+  TB_D static void noncons(const double* ul, const double* ur, int o, const EqPrm&, double* f) {
+    double rho_ll = ul[0];
+    double v1 = ul[1] / rho_ll, v2 = ul[2] / rho_ll, v3 = ul[3] / rho_ll;
+    double B1 = ul[5], B2 = ul[6], B3 = ul[7], psi_ll = ul[8];
+    double vdotB = v1 * B1 + v2 * B2 + v3 * B3;
+    double Bo_rr = (o == 1) ? ur[5] : (o == 2 ? ur[6] : ur[7]), psi_rr = ur[8];
+    double vo = (o == 1) ? v1 : (o == 2 ? v2 : v3);
+    f[0] = 0;
+    f[1] = B1 * Bo_rr; f[2] = B2 * Bo_rr; f[3] = B3 * Bo_rr;
+    f[4] = vdotB * Bo_rr + vo * psi_ll * psi_rr;
+    f[5] = v1 * Bo_rr; f[6] = v2 * Bo_rr; f[7] = v3 * Bo_rr;
+    f[8] = vo * psi_rr;
+  }
+  TB_D static void hindenlang_gassner(const double* ul, const double* ur, int o, const EqPrm& p, double* f) {
+    double ql[9], qr[9];
+    cons2prim(ul, p, ql); cons2prim(ur, p, qr);
+    hindenlang_gassner_q(ql, qr, o, p, f);
+  }
+  TB_D static void hindenlang_gassner_q(const double* ql, const double* qr, int o, const EqPrm& p, double* f) {
+    // rotate components so that the code below is written once for "normal = 1"
+    // (a, b, c) = (o, next, next-next) keeps the sign structure of the induction terms
+    const int a = o - 1, b = o % 3, c = (o + 1) % 3;
+    double val[3] = {ql[1], ql[2], ql[3]}, var[3] = {qr[1], qr[2], qr[3]};
+    double Bl[3] = {ql[5], ql[6], ql[7]}, Br[3] = {qr[5], qr[6], qr[7]};
+    double rho_ll = ql[0], rho_rr = qr[0], p_ll = ql[4], p_rr = qr[4], psl = ql[8], psr = qr[8];
+    double rho_mean = ln_mean(rho_ll, rho_rr);
+    double inv_rho_p_mean = p_ll * p_rr * inv_ln_mean(rho_ll * p_rr, rho_rr * p_ll);
+    double vavg[3] = {0.5 * (val[0] + var[0]), 0.5 * (val[1] + var[1]), 0.5 * (val[2] + var[2])};
+    double p_avg = 0.5 * (p_ll + p_rr), psi_avg = 0.5 * (psl + psr);
+    double vsq = 0.5 * (val[0] * var[0] + val[1] * var[1] + val[2] * var[2]);
+    double msq = 0.5 * (Bl[0] * Br[0] + Bl[1] * Br[1] + Bl[2] * Br[2]);
+    const double igm1 = 1.0 / (p.gamma - 1);
+    double f1 = rho_mean * vavg[a];
+    double fm[3], fB[3];
+    fm[a] = f1 * vavg[a] + p_avg + msq - 0.5 * (Bl[a] * Br[a] + Br[a] * Bl[a]);
+    fm[b] = f1 * vavg[b] - 0.5 * (Bl[a] * Br[b] + Br[a] * Bl[b]);
+    fm[c] = f1 * vavg[c] - 0.5 * (Bl[a] * Br[c] + Br[a] * Bl[c]);
+    fB[a] = p.c_h * psi_avg;
+    fB[b] = 0.5 * (val[a] * Bl[b] - val[b] * Bl[a] + var[a] * Br[b] - var[b] * Br[a]);
+    fB[c] = 0.5 * (val[a] * Bl[c] - val[c] * Bl[a] + var[a] * Br[c] - var[c] * Br[a]);
+    // energy: the (b, c) transverse pairs enter symmetrically, in Trixi's order (lower index first)
+    const int t1 = b < c ? b : c, t2 = b < c ? c : b;
+    double f5 = f1 * (vsq + inv_rho_p_mean * igm1) +
+                0.5 * (+p_ll * var[a] + p_rr * val[a] + (val[a] * Bl[t1] * Br[t1] + var[a] * Br[t1] * Bl[t1]) +
+                       (val[a] * Bl[t2] * Br[t2] + var[a] * Br[t2] * Bl[t2]) -
+                       (val[t1] * Bl[a] * Br[t1] + var[t1] * Br[a] * Bl[t1]) -
+                       (val[t2] * Bl[a] * Br[t2] + var[t2] * Br[a] * Bl[t2]) + p.c_h * (Bl[a] * psr + Br[a] * psl));
+    f[0] = f1; f[1] = fm[0]; f[2] = fm[1]; f[3] = fm[2]; f[4] = f5;
+    f[5] = fB[0]; f[6] = fB[1]; f[7] = fB[2];
+    f[8] = p.c_h * 0.5 * (Bl[a] + Br[a]);
+  }
+  TB_D static void two_point(int kind, const double* ul, const double* ur, int o, const EqPrm& p, double* f) {
+    if (kind == TRIXIB200_FLUX_HINDENLANG_GASSNER) { hindenlang_gassner(ul, ur, o, p, f); return; }
+    double fl[9], fr[9];
+    flux(ul, o, p, fl); flux(ur, o, p, fr);
+    if (kind == TRIXIB200_FLUX_CENTRAL) {
+#pragma unroll
+      for (int v = 0; v < 9; ++v) f[v] = 0.5 * (fl[v] + fr[v]);
+      return;
+    }
+    double cl = fast_wavespeed(ul, o, p), cr = fast_wavespeed(ur, o, p);
+    double vl = ((o == 1) ? ul[1] : (o == 2 ? ul[2] : ul[3])) / ul[0], vr = ((o == 1) ? ur[1] : (o == 2 ? ur[2] : ur[3])) / ur[0];
+    if (kind == TRIXIB200_FLUX_LAX_FRIEDRICHS || kind == TRIXIB200_FLUX_LAX_FRIEDRICHS_NAIVE) {
+      double lam = (kind == TRIXIB200_FLUX_LAX_FRIEDRICHS_NAIVE) ? fmax(fabs(vl), fabs(vr)) + fmax(cl, cr)
+                                                               : fmax(fabs(vl) + cl, fabs(vr) + cr);
+#pragma unroll
+      for (int v = 0; v < 9; ++v) f[v] = 0.5 * (fl[v] + fr[v]) + (-0.5 * lam * (ur[v] - ul[v]));
+      return;
+    }
+    // HLLE: FluxHLL(min_max_speed_einfeldt)
+    double vroe, croe;
+    fast_wavespeed_roe(ul, ur, o, p, vroe, croe);
+    double lmin = fmin(vl - cl, vroe - croe), lmax = fmax(vr + cr, vroe + croe);
+    if (lmin >= 0 && lmax >= 0) {
+#pragma unroll
+      for (int v = 0; v < 9; ++v) f[v] = fl[v];
+    } else if (lmax <= 0 && lmin <= 0) {
+#pragma unroll
+      for (int v = 0; v < 9; ++v) f[v] = fr[v];
+    } else {
+      double inv = 1.0 / (lmax - lmin);
+      double fac_ll = lmax * inv, fac_rr = lmin * inv, fac_d = lmin * lmax * inv;
+#pragma unroll
+      for (int v = 0; v < 9; ++v) f[v] = fac_ll * fl[v] - fac_rr * fr[v] + fac_d * (ur[v] - ul[v]);
+    }
+  }
+  TB_D static void to_q(const double* u, const EqPrm& p, double* q) { cons2prim(u, p, q); }
+  TB_D static void two_point_q(int kind, const double* ql, const double* qr, int o, const EqPrm& p, double* f) {
+    if (kind == TRIXIB200_FLUX_HINDENLANG_GASSNER) { hindenlang_gassner_q(ql, qr, o, p, f); return; }
+    double ul[9], ur[9];
+    prim2cons(ql, p, ul); prim2cons(qr, p, ur);
+    two_point(kind, ul, ur, o, p, f);
+  }
+  // flux_nonconservative_powell on primitive variables (only v, B, psi of the first argument enter)
+  TB_D static void noncons_q(const double* ql, const double* qr, int o, const EqPrm&, double* f) {
+    double v1 = ql[1], v2 = ql[2], v3 = ql[3];
+    double B1 = ql[5], B2 = ql[6], B3 = ql[7], psi_ll = ql[8];
+    double vdotB = v1 * B1 + v2 * B2 + v3 * B3;
+    double Bo_rr = (o == 1) ? qr[5] : (o == 2 ? qr[6] : qr[7]), psi_rr = qr[8];
+    double vo = (o == 1) ? v1 : (o == 2 ? v2 : v3);
+    f[0] = 0;
+    f[1] = B1 * Bo_rr; f[2] = B2 * Bo_rr; f[3] = B3 * Bo_rr;
+    f[4] = vdotB * Bo_rr + vo * psi_ll * psi_rr;
+    f[5] = v1 * Bo_rr; f[6] = v2 * Bo_rr; f[7] = v3 * Bo_rr;
+    f[8] = vo * psi_rr;
+  }
+  TB_D static void max_abs_speeds(const double* u, const EqPrm& p, double* lam) {
+#pragma unroll
+    for (int d = 0; d < 3; ++d) lam[d] = fabs(u[1 + d] / u[0]) + fast_wavespeed(u, d + 1, p);
+  }
+  TB_D static double indicator_var(int kind, const double* u, const EqPrm& p) {
+    double q[9];
+    cons2prim(u, p, q);
+    return kind == TRIXIB200_IND_DENSITY ? q[0] : (kind == TRIXIB200_IND_PRESSURE ? q[4] : q[0] * q[4]);
+  }
+  TB_D static void prim2cons(const double* q, const EqPrm& p, double* u) {
+    u[0] = q[0]; u[1] = q[0] * q[1]; u[2] = q[0] * q[2]; u[3] = q[0] * q[3];
+    u[5] = q[5]; u[6] = q[6]; u[7] = q[7]; u[8] = q[8];
+    u[4] = q[4] / (p.gamma - 1) + 0.5 * (u[1] * q[1] + u[2] * q[2] + u[3] * q[3]) +
+           0.5 * (q[5] * q[5] + q[6] * q[6] + q[7] * q[7]) + 0.5 * q[8] * q[8];
+  }
+  TB_D static void initial_condition(int ic, const double* x, double t, const EqPrm& p, double* u) {
+    double q[9];
+    if (ic == TRIXIB200_IC_CONSTANT) {
+      const double q0[9] = {1.0, 0.1, -0.2, 0.3, 1.5, 0.4, -0.3, 0.2, 0.05};
+#pragma unroll
+      for (int v = 0; v < 9; ++v) q[v] = q0[v];
+      prim2cons(q, p, u);
+      return;
+    }
+    if (ic == TRIXIB200_IC_WEAK_BLAST_WAVE) {
+      double r = sqrt(x[0] * x[0] + x[1] * x[1] + x[2] * x[2]);
+      double phi = atan2(x[1], x[0]);
+      double theta = (r == 0.0) ? 0.0 : acos(x[2] / r);
+      bool out = r > 0.5;
+      q[0] = out ? 1.0 : 1.1691;
+      q[1] = out ? 0.0 : 0.1882 * cos(phi) * sin(theta);
+      q[2] = out ? 0.0 : 0.1882 * sin(phi) * sin(theta);
+      q[3] = out ? 0.0 : 0.1882 * cos(theta);
+      q[4] = out ? 1.0 : 1.245;
+      q[5] = 1.0; q[6] = 1.0; q[7] = 1.0; q[8] = 0.0;
+      prim2cons(q, p, u);
+      return;
+    }
+    // Alfven wave (initial_condition_convergence_test), domain [-1,1]^3, gamma = 5/3
+    const double omega = 2.0 * M_PI, r = 2.0, e = 0.2;
+    double nx = 1 / sqrt(r * r + 1.0), ny = r / sqrt(r * r + 1.0);
+    double sqr = 1.0, Va = omega / (ny * sqr);
+    double phi_alv = omega / ny * (nx * (x[0] - 0.5 * r) + ny * (x[1] - 0.5 * r)) - Va * t;
+    q[0] = 1.0;
+    q[1] = -e * ny * cos(phi_alv) / q[0];
+    q[2] = e * nx * cos(phi_alv) / q[0];
+    q[3] = e * sin(phi_alv) / q[0];
+    q[4] = 1.0;
+    q[5] = nx - q[0] * q[1] * sqr; q[6] = ny - q[0] * q[2] * sqr; q[7] = -q[0] * q[3] * sqr; q[8] = 0.0;
+    prim2cons(q, p, u);
+  }
+  TB_D static void source(int, const double*, const double*, double, const EqPrm&, double* s) {
+#pragma unroll
+    for (int v = 0; v < 9; ++v) s[v] = 0;
+  }
+};
+
+}  // namespace tb

@@ -1,0 +1,880 @@
+// libtrixib200 host runtime: handle construction (device containers, Morton-range partition, halo plans),
+// rhs! orchestration on CUDA streams, and the C ABI declared in include/trixib200.h.
+// Replaces the reference's L0-L3 (src/solvers/cache.jl, containers_*.jl, dg_*.jl host launchers,
+// src/auxiliary/configurators.jl) -- see DESIGN.md.
+#include <cuda_runtime.h>
+#include <dlfcn.h>
+#include <algorithm>
+#include <cmath>
+#include <cstdio>
+#include <cstring>
+#include <string>
+#include <vector>
+#include "../../include/trixib200.h"
+#include "device.cuh"
+#include "kernels_staged.cuh"
+#include "kernels_fused.cuh"
+
+using namespace tb;
+
+static thread_local std::string g_err;
+static int fail(int code, const std::string& msg) { g_err = msg; return code; }
+#define CUDA_TRY(x)                                                                              \
+  do {                                                                                           \
+    cudaError_t e_ = (x);                                                                        \
+    if (e_ != cudaSuccess)                                                                       \
+      return fail(TRIXIB200_ECUDA, std::string(#x) + ": " + cudaGetErrorString(e_));             \
+  } while (0)
+
+// ---------------------------------------------------------------------------------------------- NCCL (lazy)
+typedef struct ncclComm* ncclComm_t;
+typedef struct { char internal[128]; } ncclUniqueId;
+struct Nccl {
+  void* lib = nullptr;
+  int (*GetUniqueId)(ncclUniqueId*) = nullptr;
+  int (*CommInitRank)(ncclComm_t*, int, ncclUniqueId, int) = nullptr;
+  int (*CommDestroy)(ncclComm_t) = nullptr;
+  int (*Send)(const void*, size_t, int, int, ncclComm_t, cudaStream_t) = nullptr;
+  int (*Recv)(void*, size_t, int, int, ncclComm_t, cudaStream_t) = nullptr;
+  int (*AllReduce)(const void*, void*, size_t, int, int, ncclComm_t, cudaStream_t) = nullptr;
+  int (*GroupStart)() = nullptr;
+  int (*GroupEnd)() = nullptr;
+  const char* (*GetErrorString)(int) = nullptr;
+  bool load() {
+    if (lib) return true;
+    // RTLD_NOLOAD first: reuse the libnccl the host process (e.g. PyTorch) already mapped
+    lib = dlopen("libnccl.so.2", RTLD_NOW | RTLD_NOLOAD);
+    if (!lib) lib = dlopen("libnccl.so.2", RTLD_NOW);
+    if (!lib) lib = dlopen("libnccl.so", RTLD_NOW);
+    if (!lib) return false;
+#define SYM(n) *(void**)(&n) = dlsym(lib, "nccl" #n)
+    SYM(GetUniqueId); SYM(CommInitRank); SYM(CommDestroy); SYM(Send); SYM(Recv); SYM(AllReduce);
+    SYM(GroupStart); SYM(GroupEnd); SYM(GetErrorString);
+#undef SYM
+    return GetUniqueId && CommInitRank && Send && Recv && AllReduce && GroupStart && GroupEnd;
+  }
+};
+static Nccl g_nccl;
+constexpr int NCCL_FLOAT64 = 8, NCCL_MAX = 2;
+
+
+// ---------------------------------------------------------------------------------------------- partition plan
+// Pure host logic (no CUDA): contiguous range of the leaf (Morton) order per rank, local interface list, halo
+// send/recv plan and the per-element face neighbour table. Exposed through trixib200_plan_* so the N>1 host
+// logic can be tested on CPU-only machines.
+struct Plan {
+  int nd = 0, nsmall = 0;
+  int64_t EG = 0, first = 0, last = 0;
+  std::vector<int> if_left, if_right, if_dim;         // local interfaces (halo side = halo code)
+  std::vector<int64_t> if_global;                      // global interface index of each local interface
+  std::vector<int> face_nbr;                           // [E, 2*nd]
+  std::vector<int> send_elem, send_dir;                // peer-major send list (local element, 0-based direction)
+  std::vector<int64_t> send_global_iface;              // global interface index of each send entry
+  std::vector<int> peers;
+  std::vector<int64_t> peer_count;
+  std::vector<int> elems_interior, elems_halo;
+  std::vector<int> bd_elem, bd_dim, bd_side, bd_dir;
+  std::vector<int64_t> bd_global;
+  std::vector<int> mo_ids, mo_side, mo_dim;
+};
+
+static int64_t range_first(int64_t EG, int nranks, int r) { return (int64_t)((__int128)EG * r / nranks); }
+
+static int build_plan(const trixib200_config& c, const trixib200_mesh_host* ms, Plan& P) {
+  const int nd = c.ndim;
+  P.nd = nd;
+  P.nsmall = nd == 3 ? 4 : (nd == 2 ? 2 : 0);
+  const int64_t EG = ms->nelements;
+  P.EG = EG;
+  if (c.nranks < 1 || c.rank < 0 || c.rank >= c.nranks) return fail(TRIXIB200_EINVAL, "bad rank/nranks");
+  if (EG < c.nranks) return fail(TRIXIB200_EINVAL, "fewer elements than ranks");
+  const int64_t first = range_first(EG, c.nranks, c.rank), last = range_first(EG, c.nranks, c.rank + 1);
+  P.first = first; P.last = last;
+  const int64_t E = last - first;
+  if (E >= (int64_t)1 << 30) return fail(TRIXIB200_EUNSUPPORTED, "too many elements per rank for int32 ids");
+  auto owner = [&](int64_t g) {
+    int r = (int)(((__int128)(g + 1) * c.nranks - 1) / EG);
+    while (r > 0 && range_first(EG, c.nranks, r) > g) --r;
+    while (r + 1 < c.nranks && range_first(EG, c.nranks, r + 1) <= g) ++r;
+    return r;
+  };
+  P.face_nbr.assign((size_t)E * 2 * nd, NB_SFV);
+  std::vector<std::vector<int>> send_elem(c.nranks), send_dir(c.nranks);
+  std::vector<std::vector<int64_t>> send_gi(c.nranks);
+  struct HaloRef { int64_t iface; int peer; int64_t k; };
+  std::vector<HaloRef> halos;
+  std::vector<int64_t> per_peer(c.nranks, 0);
+  for (int64_t s = 0; s < ms->ninterfaces; ++s) {
+    int64_t L = ms->interfaces_neighbor_ids[2 * s] - 1, R = ms->interfaces_neighbor_ids[2 * s + 1] - 1;
+    int dim = (int)ms->interfaces_orientations[s] - 1;
+    if (L < 0 || L >= EG || R < 0 || R >= EG || dim < 0 || dim >= nd) return fail(TRIXIB200_EINVAL, "bad interface entry");
+    bool lin = L >= first && L < last, rin = R >= first && R < last;
+    if (!lin && !rin) continue;
+    P.if_global.push_back(s);
+    if (lin && rin) {
+      P.if_left.push_back((int)(L - first)); P.if_right.push_back((int)(R - first)); P.if_dim.push_back(dim);
+      P.face_nbr[(size_t)(L - first) * 2 * nd + 2 * dim + 1] = (int)(R - first);
+      P.face_nbr[(size_t)(R - first) * 2 * nd + 2 * dim] = (int)(L - first);
+    } else {
+      int peer = owner(lin ? R : L);
+      int64_t k = per_peer[peer]++;
+      halos.push_back({(int64_t)P.if_left.size(), peer, k});
+      send_gi[peer].push_back(s);
+      if (lin) {
+        P.if_left.push_back((int)(L - first)); P.if_right.push_back(0); P.if_dim.push_back(dim);
+        send_elem[peer].push_back((int)(L - first)); send_dir[peer].push_back(2 * dim + 1);
+      } else {
+        P.if_left.push_back(0); P.if_right.push_back((int)(R - first)); P.if_dim.push_back(dim);
+        send_elem[peer].push_back((int)(R - first)); send_dir[peer].push_back(2 * dim);
+      }
+    }
+  }
+  // halo slots are peer-major; the k-th face exchanged with a peer has the same k on both sides because both
+  // ranks walk the global interface list in the same order
+  std::vector<int64_t> peer_off(c.nranks + 1, 0);
+  for (int p = 0; p < c.nranks; ++p) peer_off[p + 1] = peer_off[p] + per_peer[p];
+  for (int p = 0; p < c.nranks; ++p)
+    if (per_peer[p] > 0) { P.peers.push_back(p); P.peer_count.push_back(per_peer[p]); }
+  for (int p = 0; p < c.nranks; ++p) {
+    P.send_elem.insert(P.send_elem.end(), send_elem[p].begin(), send_elem[p].end());
+    P.send_dir.insert(P.send_dir.end(), send_dir[p].begin(), send_dir[p].end());
+    P.send_global_iface.insert(P.send_global_iface.end(), send_gi[p].begin(), send_gi[p].end());
+  }
+  std::vector<char> touches_halo(E, 0);
+  for (const HaloRef& hr : halos) {
+    int64_t slot = peer_off[hr.peer] + hr.k;
+    if (slot >= ((int64_t)1 << 30)) return fail(TRIXIB200_EUNSUPPORTED, "too many halo faces");
+    int code = nb_from_halo_slot((int)slot);
+    int64_t s = hr.iface;
+    int dim = P.if_dim[s];
+    int le = send_elem[hr.peer][hr.k], ldir = send_dir[hr.peer][hr.k];
+    if (ldir == 2 * dim + 1) P.if_right[s] = code; else P.if_left[s] = code;
+    P.face_nbr[(size_t)le * 2 * nd + ldir] = code;
+    touches_halo[le] = 1;
+  }
+  for (int64_t e = 0; e < E; ++e) (touches_halo[e] ? P.elems_halo : P.elems_interior).push_back((int)e);
+  // boundaries (sorted by direction; keep only local ones, order preserved)
+  int64_t b = 0;
+  for (int dir = 0; dir < 2 * nd; ++dir) {
+    int64_t nb = ms->nboundaries > 0 ? ms->n_boundaries_per_direction[dir] : 0;
+    if (nb > 0 && c.boundary_conditions[dir] == TRIXIB200_BC_PERIODIC)
+      return fail(TRIXIB200_EINVAL, "mesh has a non-periodic boundary in a direction whose boundary condition is periodic");
+    for (int64_t k = 0; k < nb; ++k, ++b) {
+      int64_t g = ms->boundaries_neighbor_ids[b] - 1;
+      if (g < first || g >= last) continue;
+      P.bd_elem.push_back((int)(g - first));
+      P.bd_dim.push_back((int)ms->boundaries_orientations[b] - 1);
+      P.bd_side.push_back((int)ms->boundaries_neighbor_sides[b]);
+      P.bd_dir.push_back(dir);
+      P.bd_global.push_back(b);
+    }
+  }
+  if (b != ms->nboundaries) return fail(TRIXIB200_EINVAL, "n_boundaries_per_direction does not sum to nboundaries");
+  // mortars
+  const int rows = P.nsmall + 1;
+  for (int64_t m = 0; m < ms->nmortars; ++m) {
+    for (int r = 0; r < rows; ++r) {
+      int64_t g = ms->mortars_neighbor_ids[rows * m + r] - 1;
+      if (g < first || g >= last) return fail(TRIXIB200_EUNSUPPORTED, "mortar crosses a partition boundary");
+      P.mo_ids.push_back((int)(g - first));
+    }
+    P.mo_side.push_back((int)ms->mortars_large_sides[m]);
+    P.mo_dim.push_back((int)ms->mortars_orientations[m] - 1);
+  }
+  return 0;
+}
+
+extern "C" int trixib200_plan_create(const trixib200_config* cfg, const trixib200_mesh_host* mesh, void** out) {
+  if (!cfg || !mesh || !out) return fail(TRIXIB200_EINVAL, "null argument");
+  Plan* P = new Plan();
+  int rc = build_plan(*cfg, mesh, *P);
+  if (rc) { delete P; *out = nullptr; return rc; }
+  *out = P;
+  return 0;
+}
+extern "C" int trixib200_plan_destroy(void* p) { delete (Plan*)p; return 0; }
+static bool plan_array(Plan* P, const std::string& n, const void** data, int64_t* len, int* width) {
+#define PA(name, vec, w) if (n == name) { *data = P->vec.data(); *len = (int64_t)P->vec.size(); *width = w; return true; }
+  PA("if_left", if_left, 4) PA("if_right", if_right, 4) PA("if_dim", if_dim, 4) PA("if_global", if_global, 8)
+  PA("face_nbr", face_nbr, 4) PA("send_elem", send_elem, 4) PA("send_dir", send_dir, 4)
+  PA("send_global_iface", send_global_iface, 8) PA("peers", peers, 4) PA("peer_count", peer_count, 8)
+  PA("elems_interior", elems_interior, 4) PA("elems_halo", elems_halo, 4) PA("bd_elem", bd_elem, 4)
+  PA("bd_global", bd_global, 8) PA("mo_ids", mo_ids, 4)
+#undef PA
+  return false;
+}
+extern "C" int64_t trixib200_plan_len(void* p, const char* name) {
+  const void* dptr; int64_t len; int w;
+  if (!p || !name) return -1;
+  std::string n(name);
+  if (n == "first_element") return ((Plan*)p)->first;
+  if (n == "nelements") return ((Plan*)p)->last - ((Plan*)p)->first;
+  if (!plan_array((Plan*)p, n, &dptr, &len, &w)) return -1;
+  return len;
+}
+// copies the named plan array widened to int64
+extern "C" int trixib200_plan_get(void* p, const char* name, int64_t* out, int64_t n) {
+  const void* dptr; int64_t len; int w;
+  if (!p || !name || !plan_array((Plan*)p, name, &dptr, &len, &w) || len != n) return fail(TRIXIB200_EINVAL, "bad plan array request");
+  for (int64_t i = 0; i < n; ++i) out[i] = (w == 4) ? (int64_t)((const int*)dptr)[i] : ((const int64_t*)dptr)[i];
+  return 0;
+}
+
+// ---------------------------------------------------------------------------------------------- handle
+struct trixib200_handle {
+  trixib200_config cfg;
+  Dev d;
+  int nsmall = 0;
+  int64_t E_global = 0, first = 0;
+  cudaStream_t stream = nullptr, comm_stream = nullptr;
+  bool owns_stream = false;
+  cudaEvent_t ev_pack = nullptr, ev_halo = nullptr, ev_a = nullptr, ev_b = nullptr;
+  std::vector<void*> allocs;
+  double* d_scalar = nullptr;
+  int64_t launches = 0;
+  bool fused = false;
+  // fused-path element lists (multi-GPU overlap): interior first, then elements touching a halo face
+  int* d_elems_interior = nullptr; int* d_elems_halo = nullptr;
+  int64_t n_interior = 0, n_halo_elems = 0;
+  // halo plan
+  std::vector<int> peers;                 // peer ranks
+  std::vector<int64_t> peer_count;        // faces exchanged with each peer (send == recv count)
+  ncclComm_t comm = nullptr;
+  int sm_count = 148;
+};
+
+template <class T> static int upload(trixib200_handle* h, const std::vector<T>& v, T** out) {
+  *out = nullptr;
+  size_t bytes = std::max<size_t>(v.size(), 1) * sizeof(T);
+  void* p = nullptr;
+  if (cudaMalloc(&p, bytes) != cudaSuccess) return fail(TRIXIB200_ENOMEM, "cudaMalloc failed (" + std::to_string(bytes) + " B)");
+  h->allocs.push_back(p);
+  if (!v.empty()) CUDA_TRY(cudaMemcpy(p, v.data(), v.size() * sizeof(T), cudaMemcpyHostToDevice));
+  *out = (T*)p;
+  return 0;
+}
+static int dalloc(trixib200_handle* h, size_t n, double** out, bool zero = true) {
+  void* p = nullptr;
+  size_t bytes = std::max<size_t>(n, 1) * sizeof(double);
+  if (cudaMalloc(&p, bytes) != cudaSuccess) return fail(TRIXIB200_ENOMEM, "cudaMalloc failed (" + std::to_string(bytes) + " B)");
+  h->allocs.push_back(p);
+  if (zero) CUDA_TRY(cudaMemset(p, 0, bytes));
+  *out = (double*)p;
+  return 0;
+}
+
+static inline unsigned nblk(int64_t n, int t) { return (unsigned)((n + t - 1) / t); }
+
+// dispatch on (equations, ndim)
+#define TB_DISPATCH_EQ(h, ...)                                                          \
+  do {                                                                                  \
+    const int nd_ = (h)->cfg.ndim;                                                      \
+    switch ((h)->cfg.equations) {                                                       \
+      case TRIXIB200_EQ_ADVECTION:                                                      \
+        if (nd_ == 1) { using Eq = EqAdvection<1>; __VA_ARGS__; }                              \
+        else if (nd_ == 2) { using Eq = EqAdvection<2>; __VA_ARGS__; }                         \
+        else { using Eq = EqAdvection<3>; __VA_ARGS__; }                                       \
+        break;                                                                          \
+      case TRIXIB200_EQ_EULER:                                                          \
+        if (nd_ == 1) { using Eq = EqEuler<1>; __VA_ARGS__; }                                  \
+        else if (nd_ == 2) { using Eq = EqEuler<2>; __VA_ARGS__; }                             \
+        else { using Eq = EqEuler<3>; __VA_ARGS__; }                                           \
+        break;                                                                          \
+      default: { using Eq = EqMhd3; __VA_ARGS__; } break;                                      \
+    }                                                                                   \
+  } while (0)
+#define TB_DISPATCH_ND(h, ...)                                                          \
+  do {                                                                                  \
+    const int nd_ = (h)->cfg.ndim;                                                      \
+    if (nd_ == 1) { constexpr int ND = 1; __VA_ARGS__; }                                       \
+    else if (nd_ == 2) { constexpr int ND = 2; __VA_ARGS__; }                                  \
+    else { constexpr int ND = 3; __VA_ARGS__; }                                                \
+  } while (0)
+
+static bool flux_supported(const trixib200_config& c, int k) {
+  if (c.equations == TRIXIB200_EQ_ADVECTION) return EqAdvection<1>::supports_flux(k);
+  if (c.equations == TRIXIB200_EQ_EULER) return EqEuler<1>::supports_flux(k);
+  return EqMhd3::supports_flux(k);
+}
+static bool flux_symmetric(int k) {
+  return k == TRIXIB200_FLUX_CENTRAL || k == TRIXIB200_FLUX_RANOCHA || k == TRIXIB200_FLUX_SHIMA_ETAL ||
+         k == TRIXIB200_FLUX_HINDENLANG_GASSNER;
+}
+
+// ---------------------------------------------------------------------------------------------- create
+extern "C" const char* trixib200_last_error(void) { return g_err.c_str(); }
+extern "C" int trixib200_version(void) { return 100; }
+
+extern "C" int trixib200_destroy(trixib200_handle* h) {
+  if (!h) return 0;
+  cudaSetDevice(h->cfg.device);
+  if (h->stream) cudaStreamSynchronize(h->stream);
+  if (h->comm && g_nccl.CommDestroy) g_nccl.CommDestroy(h->comm);
+  for (void* p : h->allocs) cudaFree(p);
+  if (h->ev_pack) cudaEventDestroy(h->ev_pack);
+  if (h->ev_halo) cudaEventDestroy(h->ev_halo);
+  if (h->ev_a) cudaEventDestroy(h->ev_a);
+  if (h->ev_b) cudaEventDestroy(h->ev_b);
+  if (h->comm_stream) cudaStreamDestroy(h->comm_stream);
+  if (h->stream && h->owns_stream) cudaStreamDestroy(h->stream);
+  delete h;
+  return 0;
+}
+
+static int create_impl(const trixib200_config* cfg, const trixib200_basis_host* bs, const trixib200_mesh_host* ms,
+                       trixib200_handle* h) {
+  const trixib200_config& c = *cfg;
+  // ---- validation: clear errors for anything un-enumerated, never a fallback
+  if (c.ndim < 1 || c.ndim > 3) return fail(TRIXIB200_EINVAL, "ndim must be 1, 2 or 3");
+  if (c.equations < 0 || c.equations > 2) return fail(TRIXIB200_EUNSUPPORTED, "unknown equations id");
+  if (c.equations == TRIXIB200_EQ_MHD && c.ndim != 3) return fail(TRIXIB200_EUNSUPPORTED, "IdealGlmMhdEquations only in 3D");
+  if (bs->nnodes != c.polydeg + 1) return fail(TRIXIB200_EINVAL, "basis.nnodes != polydeg + 1");
+  if (bs->nnodes < 2 || bs->nnodes > MAXN) return fail(TRIXIB200_EUNSUPPORTED, "polydeg must be in 1..7");
+  if (c.volume_integral < 0 || c.volume_integral > 2) return fail(TRIXIB200_EUNSUPPORTED, "unknown volume integral");
+  if (!flux_supported(c, c.surface_flux)) return fail(TRIXIB200_EUNSUPPORTED, "surface_flux not available for these equations");
+  if (c.volume_integral != TRIXIB200_VI_WEAK_FORM) {
+    if (!flux_supported(c, c.volume_flux)) return fail(TRIXIB200_EUNSUPPORTED, "volume_flux not available for these equations");
+    if (!flux_symmetric(c.volume_flux))
+      return fail(TRIXIB200_EUNSUPPORTED, "flux differencing needs a symmetric two-point volume flux");
+  }
+  if (c.volume_integral == TRIXIB200_VI_SHOCK_CAPTURING_HG) {
+    if (!flux_supported(c, c.volume_flux_fv)) return fail(TRIXIB200_EUNSUPPORTED, "volume_flux_fv not available for these equations");
+    if (c.equations == TRIXIB200_EQ_ADVECTION) return fail(TRIXIB200_EUNSUPPORTED, "shock capturing needs Euler or MHD");
+  }
+  if (c.nonconservative && c.equations != TRIXIB200_EQ_MHD)
+    return fail(TRIXIB200_EUNSUPPORTED, "nonconservative terms only for IdealGlmMhdEquations3D (flux_nonconservative_powell)");
+  if (c.equations == TRIXIB200_EQ_MHD && !c.nonconservative)
+    return fail(TRIXIB200_EUNSUPPORTED, "IdealGlmMhdEquations3D requires (flux, flux_nonconservative_powell) tuples");
+  if (c.source_terms != TRIXIB200_SRC_NONE && c.equations != TRIXIB200_EQ_EULER)
+    return fail(TRIXIB200_EUNSUPPORTED, "source_terms_convergence_test only for compressible Euler");
+  if (c.nranks < 1 || c.rank < 0 || c.rank >= c.nranks) return fail(TRIXIB200_EINVAL, "bad rank/nranks");
+  if (ms->nelements < c.nranks) return fail(TRIXIB200_EINVAL, "fewer elements than ranks");
+  if (c.nranks > 1 && ms->nmortars > 0) return fail(TRIXIB200_EUNSUPPORTED, "multi-GPU with mortars is not supported yet");
+  if (c.nranks > 1 && c.volume_integral == TRIXIB200_VI_SHOCK_CAPTURING_HG && c.alpha_smooth)
+    return fail(TRIXIB200_EUNSUPPORTED, "multi-GPU shock capturing with alpha_smooth is not supported yet");
+
+  int ndev = 0;
+  if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0)
+    return fail(TRIXIB200_ECUDA, "no CUDA device available (libtrixib200 has no CPU fallback)");
+  if (c.device < 0 || c.device >= ndev) return fail(TRIXIB200_EINVAL, "bad device ordinal");
+  CUDA_TRY(cudaSetDevice(c.device));
+  cudaDeviceProp prop;
+  CUDA_TRY(cudaGetDeviceProperties(&prop, c.device));
+  h->sm_count = prop.multiProcessorCount;
+  h->cfg = c;
+  CUDA_TRY(cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking));
+  h->owns_stream = true;
+  CUDA_TRY(cudaStreamCreateWithFlags(&h->comm_stream, cudaStreamNonBlocking));
+  CUDA_TRY(cudaEventCreateWithFlags(&h->ev_pack, cudaEventDisableTiming));
+  CUDA_TRY(cudaEventCreateWithFlags(&h->ev_halo, cudaEventDisableTiming));
+  CUDA_TRY(cudaEventCreate(&h->ev_a));
+  CUDA_TRY(cudaEventCreate(&h->ev_b));
+
+  const int nd = c.ndim, N = bs->nnodes;
+  Dev& d = h->d;
+  std::memset(&d, 0, sizeof(d));
+  d.ndim = nd; d.N = N;
+  d.nn = 1; for (int q = 0; q < nd; ++q) d.nn *= N;
+  d.nf = d.nn / N;
+  d.nv = c.equations == TRIXIB200_EQ_ADVECTION ? 1 : (c.equations == TRIXIB200_EQ_EULER ? nd + 2 : 9);
+  h->nsmall = nd == 3 ? 4 : (nd == 2 ? 2 : 0);
+
+  // ---- operators
+  Ops ops;
+  std::memset(&ops, 0, sizeof(ops));
+  for (int i = 0; i < N; ++i) { ops.nodes[i] = bs->nodes[i]; ops.weights[i] = bs->weights[i]; ops.inv_w[i] = bs->inverse_weights[i]; }
+  auto cpm = [&](double* dst, const double* src) { if (src) for (int i = 0; i < N * N; ++i) dst[i] = src[i]; };
+  cpm(ops.Dhat, bs->derivative_dhat); cpm(ops.Dsplit, bs->derivative_split); cpm(ops.invV, bs->inverse_vandermonde_legendre);
+  cpm(ops.fwd_u, bs->forward_upper); cpm(ops.fwd_l, bs->forward_lower); cpm(ops.rev_u, bs->reverse_upper); cpm(ops.rev_l, bs->reverse_lower);
+  ops.factor_1 = bs->boundary_interpolation[0];
+  ops.factor_2 = bs->boundary_interpolation[(N - 1) + N * 1];
+  if (ms->nmortars > 0 && (!bs->forward_upper || !bs->forward_lower || !bs->reverse_upper || !bs->reverse_lower))
+    return fail(TRIXIB200_EINVAL, "mesh has mortars but mortar operators are NULL");
+  if (c.volume_integral == TRIXIB200_VI_SHOCK_CAPTURING_HG && !bs->inverse_vandermonde_legendre)
+    return fail(TRIXIB200_EINVAL, "shock capturing needs inverse_vandermonde_legendre");
+  {
+    std::vector<Ops> v(1, ops);
+    Ops* p;
+    if (int rc = upload(h, v, &p)) return rc;
+    d.ops = p;
+  }
+
+  // ---- partition plan (host) and its upload
+  Plan P;
+  if (int rc = build_plan(c, ms, P)) return rc;
+  const int64_t EG = P.EG, first = P.first, last = P.last, E = last - first;
+  h->E_global = EG; h->first = first;
+  d.E = E;
+  if ((int64_t)d.nn * E * d.nv >= (int64_t)1 << 40) return fail(TRIXIB200_EUNSUPPORTED, "partition too large");
+  h->peers = P.peers; h->peer_count = P.peer_count;
+
+  // ---- elements
+  {
+    std::vector<double> ij(ms->inverse_jacobian + first, ms->inverse_jacobian + last);
+    double* p;
+    if (int rc = upload(h, ij, &p)) return rc;
+    d.inv_jac = p;
+    if (ms->node_coordinates) {
+      size_t per = (size_t)nd * d.nn;
+      std::vector<double> nc(ms->node_coordinates + per * first, ms->node_coordinates + per * last);
+      if (int rc = upload(h, nc, &p)) return rc;
+      d.node_coords = p;
+    }
+    if (ms->cell_centers) {
+      std::vector<double> cc(ms->cell_centers + (size_t)nd * first, ms->cell_centers + (size_t)nd * last);
+      if (int rc = upload(h, cc, &p)) return rc;
+      d.centers = p;
+    }
+    if (!ms->node_coordinates && !ms->cell_centers && (c.source_terms != TRIXIB200_SRC_NONE))
+      return fail(TRIXIB200_EINVAL, "source terms need node_coordinates or cell_centers");
+  }
+  // ---- interfaces + halo
+  d.I = (int64_t)P.if_left.size();
+  d.nhalo_recv = d.nhalo_send = (int64_t)P.send_elem.size();
+  {
+    int* p;
+    if (int rc = upload(h, P.if_left, &p)) return rc; d.if_left = p;
+    if (int rc = upload(h, P.if_right, &p)) return rc; d.if_right = p;
+    if (int rc = upload(h, P.if_dim, &p)) return rc; d.if_dim = p;
+    if (int rc = upload(h, P.send_elem, &p)) return rc; d.send_elem = p;
+    if (int rc = upload(h, P.send_dir, &p)) return rc; d.send_dir = p;
+    double* q;
+    if (int rc = dalloc(h, (size_t)d.nv * d.nf * d.nhalo_send, &q)) return rc; d.halo_send = q;
+    if (int rc = dalloc(h, (size_t)d.nv * d.nf * d.nhalo_recv, &q)) return rc; d.halo_recv = q;
+  }
+  // ---- boundaries
+  {
+    std::vector<double> bco;
+    size_t per = (size_t)nd * d.nf;
+    for (int64_t gb : P.bd_global) {
+      if (!ms->boundaries_node_coordinates) return fail(TRIXIB200_EINVAL, "boundaries need node_coordinates");
+      bco.insert(bco.end(), ms->boundaries_node_coordinates + per * gb, ms->boundaries_node_coordinates + per * (gb + 1));
+    }
+    d.B = (int64_t)P.bd_elem.size();
+    int* p; double* q;
+    if (int rc = upload(h, P.bd_elem, &p)) return rc; d.bd_elem = p;
+    if (int rc = upload(h, P.bd_dim, &p)) return rc; d.bd_dim = p;
+    if (int rc = upload(h, P.bd_side, &p)) return rc; d.bd_side = p;
+    if (int rc = upload(h, P.bd_dir, &p)) return rc; d.bd_dir = p;
+    if (int rc = upload(h, bco, &q)) return rc; d.bd_coords = q;
+    if (int rc = dalloc(h, (size_t)2 * d.nv * d.nf * d.B, &q)) return rc; d.boundaries_u = q;
+  }
+  // ---- mortars
+  {
+    d.M = (int64_t)P.mo_side.size();
+    int* p; double* q;
+    if (int rc = upload(h, P.mo_ids, &p)) return rc; d.mo_ids = p;
+    if (int rc = upload(h, P.mo_side, &p)) return rc; d.mo_side = p;
+    if (int rc = upload(h, P.mo_dim, &p)) return rc; d.mo_dim = p;
+    for (int k = 0; k < h->nsmall; ++k) {
+      if (int rc = dalloc(h, (size_t)2 * d.nv * d.nf * d.M, &q)) return rc; d.mortar_u[k] = q;
+      if (int rc = dalloc(h, (size_t)d.nv * d.nf * d.M, &q)) return rc; d.fstar_p[k] = q;
+      if (int rc = dalloc(h, (size_t)d.nv * d.nf * d.M, &q)) return rc; d.fstar_s[k] = q;
+    }
+  }
+
+  // ---- physics parameters
+  d.prm.gamma = c.gamma; d.prm.c_h = c.c_h;
+  for (int q = 0; q < 3; ++q) d.prm.a[q] = c.advection_velocity[q];
+  d.volume_integral = c.volume_integral; d.vol_flux = c.volume_flux; d.fv_flux = c.volume_flux_fv;
+  d.surf_flux = c.surface_flux; d.noncons = c.nonconservative; d.ic = c.initial_condition; d.src = c.source_terms;
+  d.ind_var = c.indicator_variable; d.alpha_smooth = c.alpha_smooth;
+  for (int q = 0; q < 6; ++q) d.bc[q] = c.boundary_conditions[q];
+  d.alpha_max = c.alpha_max; d.alpha_min = c.alpha_min;
+
+  // ---- fused path availability (3D/2D, polydeg 3) and its element lists
+  h->fused = !(c.flags & TRIXIB200_FLAG_STAGED_ONLY) && fused_available(c);
+  {
+    int* p;
+    if (int rc = upload(h, P.face_nbr, &p)) return rc;
+    d.face_nbr = p;
+    h->n_interior = (int64_t)P.elems_interior.size(); h->n_halo_elems = (int64_t)P.elems_halo.size();
+    if (int rc = upload(h, P.elems_interior, &p)) return rc; h->d_elems_interior = p;
+    if (int rc = upload(h, P.elems_halo, &p)) return rc; h->d_elems_halo = p;
+  }
+
+  // ---- materialised containers: the staged path needs all of them; the fused path only what boundary /
+  // mortar faces write (surface_flux_values) -- and nothing at all on a conforming periodic mesh
+  bool need_staged_buffers = !h->fused;
+  bool need_sfv = need_staged_buffers || d.B > 0 || d.M > 0;
+  {
+    double* q;
+    if (need_staged_buffers) { if (int rc = dalloc(h, (size_t)2 * d.nv * d.nf * d.I, &q)) return rc; d.interfaces_u = q; }
+    if (need_sfv) { if (int rc = dalloc(h, (size_t)d.nv * d.nf * 2 * nd * E, &q)) return rc; d.sfv = q; }
+    if (int rc = dalloc(h, (size_t)E, &q)) return rc; d.alpha = q;
+    if (int rc = dalloc(h, (size_t)E, &q)) return rc; d.alpha_tmp = q;
+    if (int rc = dalloc(h, 8, &q)) return rc; h->d_scalar = q;
+  }
+  CUDA_TRY(cudaDeviceSynchronize());
+  return 0;
+}
+
+extern "C" int trixib200_create(const trixib200_config* cfg, const trixib200_basis_host* basis,
+                                const trixib200_mesh_host* mesh, trixib200_handle** out) {
+  if (!cfg || !basis || !mesh || !out) return fail(TRIXIB200_EINVAL, "null argument");
+  *out = nullptr;
+  trixib200_handle* h = new trixib200_handle();
+  h->cfg = *cfg;
+  int rc = create_impl(cfg, basis, mesh, h);
+  if (rc != 0) { std::string keep = g_err; trixib200_destroy(h); g_err = keep; return rc; }
+  *out = h;
+  return 0;
+}
+
+extern "C" int64_t trixib200_size(const trixib200_handle* h, const char* name) {
+  if (!h || !name) return -1;
+  std::string n(name);
+  const Dev& d = h->d;
+  if (n == "nelements") return d.E;
+  if (n == "nelements_global") return h->E_global;
+  if (n == "first_element") return h->first;
+  if (n == "nvars") return d.nv;
+  if (n == "nnodes") return d.N;
+  if (n == "ndofs") return d.E * d.nn;
+  if (n == "nunknowns") return d.E * d.nn * d.nv;
+  if (n == "ninterfaces") return d.I;
+  if (n == "nboundaries") return d.B;
+  if (n == "nmortars") return d.M;
+  if (n == "nhalo_faces") return d.nhalo_recv;
+  if (n == "fused") return h->fused ? 1 : 0;
+  if (n == "npeers") return (int64_t)h->peers.size();
+  return -1;
+}
+
+// ---------------------------------------------------------------------------------------------- stages
+#define LAUNCH(h, kern, n, threads, smem, ...)                                       \
+  do {                                                                               \
+    if ((n) > 0) {                                                                   \
+      kern<<<nblk((n), (threads)), (threads), (smem), (h)->stream>>>(__VA_ARGS__);   \
+      (h)->launches++;                                                               \
+    }                                                                                \
+  } while (0)
+
+static int st_indicator(trixib200_handle* h, const double* u) {
+  Dev& d = h->d;
+  int threads = ((d.nn + 31) / 32) * 32;
+  TB_DISPATCH_EQ(h, { if (d.E > 0) { k_indicator<Eq><<<(unsigned)d.E, threads, 2 * d.nn * sizeof(double), h->stream>>>(d, u); h->launches++; } });
+  if (d.alpha_smooth) {
+    LAUNCH(h, k_alpha_smooth_interfaces, d.I, 256, 0, d);
+    LAUNCH(h, k_alpha_smooth_mortars, d.M, 128, 0, d, h->nsmall);
+  }
+  return 0;
+}
+static int st_volume(trixib200_handle* h, double* du, const double* u) {
+  Dev& d = h->d;
+  if (d.volume_integral == TRIXIB200_VI_SHOCK_CAPTURING_HG) st_indicator(h, u);
+  TB_DISPATCH_EQ(h, LAUNCH(h, k_volume<Eq>, d.E * d.nn, 128, 0, d, du, u));
+  return 0;
+}
+static int st_prolong_interfaces(trixib200_handle* h, const double* u) {
+  Dev& d = h->d;
+  TB_DISPATCH_ND(h, LAUNCH(h, k_prolong_interfaces<ND>, d.I * d.nf * d.nv, 256, 0, d, u));
+  return 0;
+}
+static int st_interface_flux(trixib200_handle* h) {
+  Dev& d = h->d;
+  TB_DISPATCH_EQ(h, LAUNCH(h, k_interface_flux<Eq>, d.I * d.nf, 128, 0, d));
+  return 0;
+}
+static int st_prolong_boundaries(trixib200_handle* h, const double* u) {
+  Dev& d = h->d;
+  TB_DISPATCH_ND(h, LAUNCH(h, k_prolong_boundaries<ND>, d.B * d.nf * d.nv, 256, 0, d, u));
+  return 0;
+}
+static int st_boundary_flux(trixib200_handle* h, double t) {
+  Dev& d = h->d;
+  TB_DISPATCH_EQ(h, LAUNCH(h, k_boundary_flux<Eq>, d.B * d.nf, 128, 0, d, t));
+  return 0;
+}
+static int st_prolong_mortars(trixib200_handle* h, const double* u) {
+  Dev& d = h->d;
+  if (d.ndim == 2) LAUNCH(h, k_prolong_mortars<2>, d.M * d.nf * d.nv, 128, 0, d, u);
+  else if (d.ndim == 3) LAUNCH(h, k_prolong_mortars<3>, d.M * d.nf * d.nv, 128, 0, d, u);
+  return 0;
+}
+static int st_mortar_flux(trixib200_handle* h) {
+  Dev& d = h->d;
+  if (d.ndim == 1 || d.M == 0) return 0;
+  switch (h->cfg.equations) {
+    case TRIXIB200_EQ_ADVECTION:
+      if (d.ndim == 2) LAUNCH(h, k_mortar_flux<EqAdvection<2>>, d.M * d.nf * 2, 128, 0, d);
+      else LAUNCH(h, k_mortar_flux<EqAdvection<3>>, d.M * d.nf * 4, 128, 0, d);
+      break;
+    case TRIXIB200_EQ_EULER:
+      if (d.ndim == 2) LAUNCH(h, k_mortar_flux<EqEuler<2>>, d.M * d.nf * 2, 128, 0, d);
+      else LAUNCH(h, k_mortar_flux<EqEuler<3>>, d.M * d.nf * 4, 128, 0, d);
+      break;
+    default: LAUNCH(h, k_mortar_flux<EqMhd3>, d.M * d.nf * 4, 128, 0, d); break;
+  }
+  if (d.ndim == 2) LAUNCH(h, k_mortar_to_elements<2>, d.M * d.nf * d.nv, 128, 0, d);
+  else LAUNCH(h, k_mortar_to_elements<3>, d.M * d.nf * d.nv, 128, 0, d);
+  return 0;
+}
+static int st_epilogue(trixib200_handle* h, double* du, const double* u, double t, int flags) {
+  Dev& d = h->d;
+  TB_DISPATCH_EQ(h, LAUNCH(h, k_epilogue<Eq>, d.E * d.nn, 128, 0, d, du, u, t, flags));
+  return 0;
+}
+
+// halo exchange: pack on the main stream, NCCL send/recv on the comm stream
+static int halo_begin(trixib200_handle* h, const double* u) {
+  Dev& d = h->d;
+  if (h->cfg.nranks == 1 || d.nhalo_send == 0) return 0;
+  if (!h->comm) return fail(TRIXIB200_ECOMM, "nranks > 1 but trixib200_comm_init was not called");
+  TB_DISPATCH_ND(h, LAUNCH(h, k_pack_halo<ND>, d.nhalo_send * d.nf * d.nv, 256, 0, d, u));
+  CUDA_TRY(cudaEventRecord(h->ev_pack, h->stream));
+  CUDA_TRY(cudaStreamWaitEvent(h->comm_stream, h->ev_pack, 0));
+  size_t per = (size_t)d.nv * d.nf;
+  g_nccl.GroupStart();
+  size_t off = 0;
+  for (size_t k = 0; k < h->peers.size(); ++k) {
+    size_t cnt = per * (size_t)h->peer_count[k];
+    g_nccl.Send(d.halo_send + off, cnt, NCCL_FLOAT64, h->peers[k], h->comm, h->comm_stream);
+    g_nccl.Recv((void*)(d.halo_recv + off), cnt, NCCL_FLOAT64, h->peers[k], h->comm, h->comm_stream);
+    off += cnt;
+  }
+  int rc = g_nccl.GroupEnd();
+  if (rc != 0) return fail(TRIXIB200_ECOMM, std::string("ncclGroupEnd: ") + (g_nccl.GetErrorString ? g_nccl.GetErrorString(rc) : "?"));
+  CUDA_TRY(cudaEventRecord(h->ev_halo, h->comm_stream));
+  return 0;
+}
+static int halo_wait(trixib200_handle* h) {
+  if (h->cfg.nranks == 1 || h->d.nhalo_send == 0) return 0;
+  CUDA_TRY(cudaStreamWaitEvent(h->stream, h->ev_halo, 0));
+  return 0;
+}
+
+static int rhs_staged(trixib200_handle* h, double* du, const double* u, double t) {
+  if (int rc = halo_begin(h, u)) return rc;
+  st_volume(h, du, u);
+  if (int rc = halo_wait(h)) return rc;
+  st_prolong_interfaces(h, u);
+  st_interface_flux(h);
+  st_prolong_boundaries(h, u);
+  st_boundary_flux(h, t);
+  st_prolong_mortars(h, u);
+  st_mortar_flux(h);
+  st_epilogue(h, du, u, t, 7);
+  return 0;
+}
+
+static int rhs_fused(trixib200_handle* h, double* du, const double* u, double t) {
+  Dev& d = h->d;
+  if (int rc = halo_begin(h, u)) return rc;
+  if (d.volume_integral == TRIXIB200_VI_SHOCK_CAPTURING_HG) st_indicator(h, u);
+  // faces the fused kernel does not compute itself: boundary and mortar faces -> surface_flux_values
+  if (d.B > 0) { st_prolong_boundaries(h, u); st_boundary_flux(h, t); }
+  if (d.M > 0) { st_prolong_mortars(h, u); st_mortar_flux(h); }
+  bool multi = h->cfg.nranks > 1 && d.nhalo_send > 0;
+  if (!multi) {
+    if (int rc = fused_launch(h->cfg, d, du, u, t, nullptr, d.E, h->stream, h->sm_count)) return fail(rc, "fused launch failed");
+    h->launches++;
+  } else {
+    if (h->n_interior > 0) {
+      if (int rc = fused_launch(h->cfg, d, du, u, t, h->d_elems_interior, h->n_interior, h->stream, h->sm_count)) return fail(rc, "fused launch failed");
+      h->launches++;
+    }
+    if (int rc = halo_wait(h)) return rc;
+    if (h->n_halo_elems > 0) {
+      if (int rc = fused_launch(h->cfg, d, du, u, t, h->d_elems_halo, h->n_halo_elems, h->stream, h->sm_count)) return fail(rc, "fused launch failed");
+      h->launches++;
+    }
+  }
+  return 0;
+}
+
+extern "C" int trixib200_rhs(trixib200_handle* h, double* du, const double* u, double t) {
+  if (!h || !du || !u) return fail(TRIXIB200_EINVAL, "null argument");
+  CUDA_TRY(cudaSetDevice(h->cfg.device));
+  int rc = h->fused ? rhs_fused(h, du, u, t) : rhs_staged(h, du, u, t);
+  if (rc) return rc;
+  CUDA_TRY(cudaGetLastError());
+  return 0;
+}
+
+extern "C" int trixib200_stage(trixib200_handle* h, const char* stage, double* du, const double* u, double t) {
+  if (!h || !stage) return fail(TRIXIB200_EINVAL, "null argument");
+  if (h->fused) return fail(TRIXIB200_EINVAL, "per-stage entry points need a handle created with TRIXIB200_FLAG_STAGED_ONLY");
+  CUDA_TRY(cudaSetDevice(h->cfg.device));
+  std::string n(stage);
+  Dev& d = h->d;
+  if (n == "reset_du") CUDA_TRY(cudaMemsetAsync(du, 0, sizeof(double) * d.E * d.nn * d.nv, h->stream));
+  else if (n == "calc_volume_integral") st_volume(h, du, u);
+  else if (n == "prolong2interfaces") {
+    if (int rc = halo_begin(h, u)) return rc;
+    if (int rc = halo_wait(h)) return rc;
+    st_prolong_interfaces(h, u);
+  }
+  else if (n == "calc_interface_flux") st_interface_flux(h);
+  else if (n == "prolong2boundaries") st_prolong_boundaries(h, u);
+  else if (n == "calc_boundary_flux") st_boundary_flux(h, t);
+  else if (n == "prolong2mortars") st_prolong_mortars(h, u);
+  else if (n == "calc_mortar_flux") st_mortar_flux(h);
+  else if (n == "calc_surface_integral") st_epilogue(h, du, u, t, 1);
+  else if (n == "apply_jacobian") st_epilogue(h, du, u, t, 2);
+  else if (n == "calc_sources") st_epilogue(h, du, u, t, 4);
+  else if (n == "calc_indicator") st_indicator(h, u);
+  else return fail(TRIXIB200_EINVAL, "unknown stage " + n);
+  CUDA_TRY(cudaGetLastError());
+  CUDA_TRY(cudaStreamSynchronize(h->stream));
+  return 0;
+}
+
+static bool cache_array(const trixib200_handle* h, const std::string& n, const double** p, int64_t* len) {
+  const Dev& d = h->d;
+  int64_t face = (int64_t)d.nv * d.nf;
+  if (n == "interfaces.u") { *p = d.interfaces_u; *len = 2 * face * d.I; return d.interfaces_u != nullptr; }
+  if (n == "boundaries.u") { *p = d.boundaries_u; *len = 2 * face * d.B; return true; }
+  if (n == "surface_flux_values") { *p = d.sfv; *len = face * 2 * d.ndim * d.E; return d.sfv != nullptr; }
+  if (n == "alpha") { *p = d.alpha; *len = d.E; return true; }
+  const char* m3[4] = {"mortars.u_upper_left", "mortars.u_upper_right", "mortars.u_lower_left", "mortars.u_lower_right"};
+  const char* m2[2] = {"mortars.u_upper", "mortars.u_lower"};
+  for (int q = 0; q < 4; ++q) if (d.ndim == 3 && n == m3[q]) { *p = d.mortar_u[q]; *len = 2 * face * d.M; return true; }
+  for (int q = 0; q < 2; ++q) if (d.ndim == 2 && n == m2[q]) { *p = d.mortar_u[q]; *len = 2 * face * d.M; return true; }
+  return false;
+}
+extern "C" int64_t trixib200_cache_len(const trixib200_handle* h, const char* name) {
+  const double* p; int64_t len;
+  if (!h || !name || !cache_array(h, name, &p, &len)) return -1;
+  return len;
+}
+extern "C" int trixib200_cache_get(trixib200_handle* h, const char* name, double* out, int64_t n) {
+  const double* p; int64_t len;
+  if (!h || !name || !cache_array(h, name, &p, &len)) return fail(TRIXIB200_EINVAL, "unknown or unavailable cache array");
+  if (len != n) return fail(TRIXIB200_EINVAL, "length mismatch");
+  CUDA_TRY(cudaSetDevice(h->cfg.device));
+  CUDA_TRY(cudaStreamSynchronize(h->stream));
+  if (n > 0) CUDA_TRY(cudaMemcpy(out, p, sizeof(double) * n, cudaMemcpyDeviceToHost));
+  return 0;
+}
+
+// ---------------------------------------------------------------------------------------------- max_dt
+extern "C" int trixib200_max_dt(trixib200_handle* h, const double* u, double t, double* out_host) {
+  (void)t;
+  if (!h || !u || !out_host) return fail(TRIXIB200_EINVAL, "null argument");
+  CUDA_TRY(cudaSetDevice(h->cfg.device));
+  Dev& d = h->d;
+  // nextfloat(0.0): avoids a division by zero if the speed vanishes (reference stepsize_dg_3d.jl:22-24)
+  double init = 4.9406564584124654e-324;
+  CUDA_TRY(cudaMemcpyAsync(h->d_scalar, &init, sizeof(double), cudaMemcpyHostToDevice, h->stream));
+  int64_t warps = std::min<int64_t>(d.E, (int64_t)h->sm_count * 64);
+  TB_DISPATCH_EQ(h, LAUNCH(h, k_max_dt<Eq>, warps * 32, 256, 0, d, u, h->d_scalar));
+  if (h->cfg.nranks > 1) {
+    if (!h->comm) return fail(TRIXIB200_ECOMM, "nranks > 1 but trixib200_comm_init was not called");
+    int rc = g_nccl.AllReduce(h->d_scalar, h->d_scalar, 1, NCCL_FLOAT64, NCCL_MAX, h->comm, h->stream);
+    if (rc != 0) return fail(TRIXIB200_ECOMM, "ncclAllReduce failed");
+  }
+  double m = 0;
+  CUDA_TRY(cudaMemcpyAsync(&m, h->d_scalar, sizeof(double), cudaMemcpyDeviceToHost, h->stream));
+  CUDA_TRY(cudaStreamSynchronize(h->stream));
+  *out_host = 2 / (d.N * m);
+  return 0;
+}
+
+// ---------------------------------------------------------------------------------------------- memory etc.
+extern "C" int trixib200_alloc(trixib200_handle* h, int64_t n, double** out) {
+  if (!h || !out || n < 0) return fail(TRIXIB200_EINVAL, "bad argument");
+  CUDA_TRY(cudaSetDevice(h->cfg.device));
+  void* p = nullptr;
+  if (cudaMalloc(&p, std::max<int64_t>(n, 1) * sizeof(double)) != cudaSuccess) return fail(TRIXIB200_ENOMEM, "cudaMalloc failed");
+  *out = (double*)p;
+  return 0;
+}
+extern "C" int trixib200_free(trixib200_handle* h, double* p) {
+  if (!h) return fail(TRIXIB200_EINVAL, "null handle");
+  CUDA_TRY(cudaSetDevice(h->cfg.device));
+  CUDA_TRY(cudaFree(p));
+  return 0;
+}
+extern "C" int trixib200_upload(trixib200_handle* h, double* dst, const double* src, int64_t n) {
+  if (!h) return fail(TRIXIB200_EINVAL, "null handle");
+  CUDA_TRY(cudaSetDevice(h->cfg.device));
+  CUDA_TRY(cudaMemcpyAsync(dst, src, sizeof(double) * n, cudaMemcpyHostToDevice, h->stream));
+  CUDA_TRY(cudaStreamSynchronize(h->stream));
+  return 0;
+}
+extern "C" int trixib200_download(trixib200_handle* h, double* dst, const double* src, int64_t n) {
+  if (!h) return fail(TRIXIB200_EINVAL, "null handle");
+  CUDA_TRY(cudaSetDevice(h->cfg.device));
+  CUDA_TRY(cudaMemcpyAsync(dst, src, sizeof(double) * n, cudaMemcpyDeviceToHost, h->stream));
+  CUDA_TRY(cudaStreamSynchronize(h->stream));
+  return 0;
+}
+extern "C" int trixib200_sync(trixib200_handle* h) {
+  if (!h) return fail(TRIXIB200_EINVAL, "null handle");
+  CUDA_TRY(cudaSetDevice(h->cfg.device));
+  CUDA_TRY(cudaStreamSynchronize(h->stream));
+  CUDA_TRY(cudaStreamSynchronize(h->comm_stream));
+  return 0;
+}
+extern "C" int trixib200_set_stream(trixib200_handle* h, int64_t stream) {
+  if (!h) return fail(TRIXIB200_EINVAL, "null handle");
+  if ((cudaStream_t)(intptr_t)stream == h->stream) return 0;
+  CUDA_TRY(cudaSetDevice(h->cfg.device));
+  CUDA_TRY(cudaStreamSynchronize(h->stream));
+  if (h->owns_stream) { cudaStreamDestroy(h->stream); h->owns_stream = false; }
+  h->stream = (cudaStream_t)(intptr_t)stream;
+  return 0;
+}
+extern "C" int64_t trixib200_stream(const trixib200_handle* h) { return h ? (int64_t)(intptr_t)h->stream : 0; }
+extern "C" int64_t trixib200_launch_count(const trixib200_handle* h) { return h ? h->launches : 0; }
+
+extern "C" int trixib200_fill_initial_condition(trixib200_handle* h, double* u, double t) {
+  if (!h || !u) return fail(TRIXIB200_EINVAL, "null argument");
+  CUDA_TRY(cudaSetDevice(h->cfg.device));
+  Dev& d = h->d;
+  if (!d.node_coords && !d.centers) return fail(TRIXIB200_EINVAL, "fill_initial_condition needs node_coordinates or cell_centers");
+  TB_DISPATCH_EQ(h, LAUNCH(h, k_fill_ic<Eq>, d.E * d.nn, 128, 0, d, u, t));
+  CUDA_TRY(cudaGetLastError());
+  return 0;
+}
+
+extern "C" int trixib200_rk2n_update(trixib200_handle* h, double* u, double* tmp, const double* du, double a,
+                                     double b, double dt) {
+  if (!h || !u || !tmp || !du) return fail(TRIXIB200_EINVAL, "null argument");
+  CUDA_TRY(cudaSetDevice(h->cfg.device));
+  int64_t n = h->d.E * h->d.nn * h->d.nv;
+  if (n > 0) {
+    int64_t blocks = std::min<int64_t>((n + 255) / 256, (int64_t)h->sm_count * 16);
+    k_rk2n_update<<<(unsigned)blocks, 256, 0, h->stream>>>(u, tmp, du, a, b, dt, n);
+    h->launches++;
+  }
+  CUDA_TRY(cudaGetLastError());
+  return 0;
+}
+
+extern "C" int trixib200_time_rhs(trixib200_handle* h, double* du, const double* u, double t, int reps, float* ms) {
+  if (!h || !ms || reps < 1) return fail(TRIXIB200_EINVAL, "bad argument");
+  CUDA_TRY(cudaSetDevice(h->cfg.device));
+  CUDA_TRY(cudaStreamSynchronize(h->stream));
+  CUDA_TRY(cudaStreamSynchronize(h->comm_stream));
+  CUDA_TRY(cudaEventRecord(h->ev_a, h->stream));
+  for (int i = 0; i < reps; ++i)
+    if (int rc = trixib200_rhs(h, du, u, t)) return rc;
+  CUDA_TRY(cudaEventRecord(h->ev_b, h->stream));
+  CUDA_TRY(cudaEventSynchronize(h->ev_b));
+  CUDA_TRY(cudaEventElapsedTime(ms, h->ev_a, h->ev_b));
+  return 0;
+}
+
+// ---------------------------------------------------------------------------------------------- comm
+extern "C" int trixib200_comm_unique_id(char* id128) {
+  if (!id128) return fail(TRIXIB200_EINVAL, "null argument");
+  if (!g_nccl.load()) return fail(TRIXIB200_ECOMM, "libnccl.so.2 not found");
+  ncclUniqueId id;
+  int rc = g_nccl.GetUniqueId(&id);
+  if (rc != 0) return fail(TRIXIB200_ECOMM, "ncclGetUniqueId failed");
+  std::memcpy(id128, id.internal, 128);
+  return 0;
+}
+extern "C" int trixib200_comm_init(trixib200_handle* h, const char* id128) {
+  if (!h || !id128) return fail(TRIXIB200_EINVAL, "null argument");
+  if (h->cfg.nranks == 1) return 0;
+  if (!g_nccl.load()) return fail(TRIXIB200_ECOMM, "libnccl.so.2 not found");
+  CUDA_TRY(cudaSetDevice(h->cfg.device));
+  ncclUniqueId id;
+  std::memcpy(id.internal, id128, 128);
+  int rc = g_nccl.CommInitRank(&h->comm, h->cfg.nranks, id, h->cfg.rank);
+  if (rc != 0) return fail(TRIXIB200_ECOMM, std::string("ncclCommInitRank: ") + (g_nccl.GetErrorString ? g_nccl.GetErrorString(rc) : "?"));
+  return 0;
+}
