@@ -12,7 +12,7 @@ BOX2 = (dict(type="box", coordinates_min=(0.0, -1.0), coordinates_max=(1.0, 1.0)
 def case(ndim, equations, level=2, polydeg=3, vi="weak_form", volume_flux="flux_central",
          volume_flux_fv="flux_lax_friedrichs", surface_flux="flux_lax_friedrichs", noncons=False,
          ic="convergence_test", source="none", bc="periodic", periodic=True, patches=(), gamma=1.4,
-         adv=(0.2, -0.7, 0.5), c_h=1.0, cmin=-1.0, cmax=1.0, alpha_max=0.5, alpha_min=0.001, alpha_smooth=True,
+         adv=(0.2, -0.7, 0.9), c_h=1.0, cmin=-1.0, cmax=1.0, alpha_max=0.5, alpha_min=0.001, alpha_smooth=True,
          variable="density_pressure"):
     return dict(ndim=ndim, equations=equations, level=level, polydeg=polydeg, vi=vi, volume_flux=volume_flux,
                 volume_flux_fv=volume_flux_fv, surface_flux=surface_flux, noncons=noncons, ic=ic, source=source,

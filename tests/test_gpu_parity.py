@@ -53,11 +53,16 @@ def test_stages_match_oracle(name):
                         "mortars.u_lower_right"], 2: ["mortars.u_upper", "mortars.u_lower"], 1: []}[c["ndim"]]
     o.stage("reset_du", du_ref, u, t)
     semi.stage("reset_du", du_d, u_d, t)
+    scale = 0.0
     for st in STAGES:
         o.stage(st, du_ref, u, t)
         semi.stage(st, du_d, u_d, t)
         if st in ("calc_volume_integral", "calc_surface_integral", "apply_jacobian", "calc_sources"):
-            assert rel_max_err(du_d.cpu().numpy(), du_ref) <= TOL, st
+            # intermediate du: volume and surface terms cancel for smooth data, so the stage error is measured
+            # against the largest magnitude du has had so far (its operands), not the small remainder
+            fac = o.f64("inverse_jacobian").max() if st in ("apply_jacobian", "calc_sources") else 1.0
+            scale = max(scale, np.abs(du_ref).max() / fac)
+            assert np.abs(du_d.cpu().numpy() - du_ref).max() <= TOL * scale * fac, st
         elif st == "prolong2interfaces":
             assert np.array_equal(semi.cache("interfaces.u"), o.f64("interfaces.u")), st   # pure gather: exact
         elif st in ("calc_interface_flux", "calc_boundary_flux", "calc_mortar_flux"):

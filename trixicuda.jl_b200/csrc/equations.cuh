@@ -16,6 +16,7 @@ struct EqPrm {
   double gamma;
   double a[3];
   double c_h;
+  double inv_gm1;  // 1 / (gamma - 1)
 };
 
 TB_D double sq(double x) { return x * x; }
@@ -30,6 +31,33 @@ TB_D double inv_ln_mean(double x, double y) {
   double f2 = (x * (x - 2 * y) + y * y) / (x * (x + 2 * y) + y * y);
   if (f2 < 1.0e-4) return (2 + f2 * (2.0 / 3 + f2 * (2.0 / 5 + f2 * (2.0 / 7)))) / (x + y);
   return log(y / x) / (y - x);
+}
+
+// Branch-free reciprocal for the fused kernels: MUFU.RCP64H seed + two Newton steps (relative error ~1e-16 for
+// normal, finite inputs -- densities, pressures and their sums; no special-case handling on purpose).
+TB_D double rcp_fast(double x) {
+  double r;
+  asm("rcp.approx.ftz.f64 %0, %1;" : "=d"(r) : "d"(x));
+  double e = fma(-x, r, 1.0);
+  r = fma(r, e, r);
+  e = fma(-x, r, 1.0);
+  r = fma(r, e, r);
+  return r;
+}
+// ln_mean / inv_ln_mean with f2 = ((x-y)/(x+y))^2 (algebraically Trixi's expression) and reciprocals instead of
+// IEEE divisions on the smooth branch; the logarithmic branch keeps the exact formula.
+// rare branch (|x-y|/(x+y) >= 1e-2), kept out of line so the hot loop stays small
+__device__ __noinline__ double ln_mean_log_branch(double x, double y) { return (y - x) / log(y / x); }
+__device__ __noinline__ double inv_ln_mean_log_branch(double x, double y) { return log(y / x) / (y - x); }
+TB_D double ln_mean_fast(double x, double y) {
+  double s = x + y, r = rcp_fast(s), u = (x - y) * r, f2 = u * u;
+  if (f2 < 1.0e-4) return s * rcp_fast(fma(f2, fma(f2, fma(f2, 2.0 / 7, 2.0 / 5), 2.0 / 3), 2.0));
+  return ln_mean_log_branch(x, y);
+}
+TB_D double inv_ln_mean_fast(double x, double y) {
+  double s = x + y, r = rcp_fast(s), u = (x - y) * r, f2 = u * u;
+  if (f2 < 1.0e-4) return fma(f2, fma(f2, fma(f2, 2.0 / 7, 2.0 / 5), 2.0 / 3), 2.0) * r;
+  return inv_ln_mean_log_branch(x, y);
 }
 
 // ------------------------------------------------------------------------------------ advection
@@ -53,6 +81,10 @@ template <int ND> struct EqAdvection {
     two_point(kind, ql, qr, o, p, f);
   }
   TB_D static void noncons_q(const double*, const double*, int, const EqPrm&, double* g) { g[0] = 0; }
+  TB_D static void to_qf(const double* u, const EqPrm& p, double* q) { to_q(u, p, q); }
+  TB_D static void two_point_qf(int kind, const double* ql, const double* qr, int o, const EqPrm& p, double* f) {
+    two_point(kind, ql, qr, o, p, f);
+  }
   TB_D static void max_abs_speeds(const double*, const EqPrm& p, double* lam) {
 #pragma unroll
     for (int d = 0; d < ND; ++d) lam[d] = fabs(p.a[d]);
@@ -134,6 +166,41 @@ template <int ND> struct EqEuler {
       for (int d = 0; d < ND; ++d) f[1 + d] = f1 * vavg[d] + ((d + 1 == o) ? p_avg : 0.0);
       f[ND + 1] = p_avg * vo_avg / (p.gamma - 1) + f1 * velocity_square_avg + pv;
     }
+  }
+  // fused-kernel variants: one reciprocal per cons2prim, reciprocal-based logarithmic means, 1/(gamma-1) hoisted
+  TB_D static void to_qf(const double* u, const EqPrm& p, double* q) {
+    double r = rcp_fast(u[0]), ke = 0;
+#pragma unroll
+    for (int d = 0; d < ND; ++d) { q[1 + d] = u[1 + d] * r; ke = fma(u[1 + d], q[1 + d], ke); }
+    q[0] = u[0];
+    q[ND + 1] = (p.gamma - 1) * fma(-0.5, ke, u[ND + 1]);
+  }
+  TB_D static void two_point_qf(int kind, const double* ql, const double* qr, int o, const EqPrm& p, double* f) {
+    if (kind != TRIXIB200_FLUX_RANOCHA && kind != TRIXIB200_FLUX_SHIMA_ETAL) { two_point_q(kind, ql, qr, o, p, f); return; }
+    double p_ll = ql[ND + 1], p_rr = qr[ND + 1];
+    double vavg[ND], vsq = 0, vo_avg = 0;
+#pragma unroll
+    for (int d = 0; d < ND; ++d) {
+      vavg[d] = 0.5 * (ql[1 + d] + qr[1 + d]);
+      vsq = fma(ql[1 + d], qr[1 + d], vsq);
+      if (d + 1 == o) vo_avg = vavg[d];
+    }
+    double p_avg = 0.5 * (p_ll + p_rr);
+    double pv = 0.5 * fma(p_ll, osel(qr, o), p_rr * osel(ql, o));
+    double f1, en;
+    if (kind == TRIXIB200_FLUX_RANOCHA) {
+      double rho_mean = ln_mean_fast(ql[0], qr[0]);
+      double inv_rho_p_mean = p_ll * p_rr * inv_ln_mean_fast(ql[0] * p_rr, qr[0] * p_ll);
+      f1 = rho_mean * vo_avg;
+      en = fma(f1, fma(inv_rho_p_mean, p.inv_gm1, 0.5 * vsq), pv);
+    } else {
+      f1 = 0.5 * (ql[0] + qr[0]) * vo_avg;
+      en = fma(p_avg * vo_avg, p.inv_gm1, fma(f1, 0.5 * vsq, pv));
+    }
+    f[0] = f1;
+#pragma unroll
+    for (int d = 0; d < ND; ++d) f[1 + d] = fma(f1, vavg[d], (d + 1 == o) ? p_avg : 0.0);
+    f[ND + 1] = en;
   }
   TB_D static void to_q(const double* u, const EqPrm& p, double* q) { cons2prim(u, p, q); }
   TB_D static void two_point_q(int kind, const double* ql, const double* qr, int o, const EqPrm& p, double* f) {
@@ -444,6 +511,10 @@ struct EqMhd3 {
 #pragma unroll
       for (int v = 0; v < 9; ++v) f[v] = fac_ll * fl[v] - fac_rr * fr[v] + fac_d * (ur[v] - ul[v]);
     }
+  }
+  TB_D static void to_qf(const double* u, const EqPrm& p, double* q) { cons2prim(u, p, q); }
+  TB_D static void two_point_qf(int kind, const double* ql, const double* qr, int o, const EqPrm& p, double* f) {
+    two_point_q(kind, ql, qr, o, p, f);
   }
   TB_D static void to_q(const double* u, const EqPrm& p, double* q) { cons2prim(u, p, q); }
   TB_D static void two_point_q(int kind, const double* ql, const double* qr, int o, const EqPrm& p, double* f) {

@@ -35,7 +35,7 @@ template <class Eq, int VI> struct FusedCfg {
 };
 
 template <class Eq, int VI, int VFLUX, int SFLUX, int FFLUX, bool NONCONS>
-__global__ void __launch_bounds__(FUSED_THREADS)
+__global__ void __launch_bounds__(FUSED_THREADS, 3)
 k_fused(Dev d, double* __restrict__ du, const double* __restrict__ u, double t, const int* __restrict__ elems,
         int64_t count) {
   using C = FusedCfg<Eq, VI>;
@@ -89,7 +89,7 @@ k_fused(Dev d, double* __restrict__ du, const double* __restrict__ u, double t, 
   double un[NV], q[NV], acc[NV];
 #pragma unroll
   for (int v = 0; v < NV; ++v) { un[v] = active ? sx[NV * n + v] : 1.0; acc[v] = 0; }
-  Eq::to_q(un, d.prm, q);
+  Eq::to_qf(un, d.prm, q);
 #pragma unroll
   for (int v = 0; v < NV; ++v) sq[v * NN + n] = q[v];
   __syncthreads();
@@ -106,9 +106,9 @@ k_fused(Dev d, double* __restrict__ du, const double* __restrict__ u, double t, 
       double qo[NV], qn[NV];
 #pragma unroll
       for (int v = 0; v < NV; ++v) qo[v] = sq[v * NN + own];
-      Eq::to_q(nb, d.prm, qn);
-      if (side) Eq::two_point_q(sflux, qo, qn, dim + 1, d.prm, fl);
-      else Eq::two_point_q(sflux, qn, qo, dim + 1, d.prm, fl);
+      Eq::to_qf(nb, d.prm, qn);
+      if (side) Eq::two_point_qf(sflux, qo, qn, dim + 1, d.prm, fl);
+      else Eq::two_point_qf(sflux, qn, qo, dim + 1, d.prm, fl);
       if (NONCONS) {
         double g[NV];
         Eq::noncons_q(qo, qn, dim + 1, d.prm, g);
@@ -164,8 +164,8 @@ k_fused(Dev d, double* __restrict__ du, const double* __restrict__ u, double t, 
 #pragma unroll
         for (int v = 0; v < NV; ++v) qp[v] = sq[v * NN + np];
         // lower node first, like Trixi's flux_differencing_kernel! (i, ii > i)
-        if (pc > ic) Eq::two_point_q(vflux, q, qp, dc + 1, d.prm, f);
-        else Eq::two_point_q(vflux, qp, q, dc + 1, d.prm, f);
+        if (pc > ic) Eq::two_point_qf(vflux, q, qp, dc + 1, d.prm, f);
+        else Eq::two_point_qf(vflux, qp, q, dc + 1, d.prm, f);
         const double w = scale * op.Dsplit[ic + N * pc];
 #pragma unroll
         for (int v = 0; v < NV; ++v) { xb[v * NN + n] = f[v]; acc[v] += w * f[v]; }
@@ -231,7 +231,7 @@ k_fused(Dev d, double* __restrict__ du, const double* __restrict__ u, double t, 
           double qp[NV];
 #pragma unroll
           for (int v = 0; v < NV; ++v) qp[v] = sq[v * NN + n + st];
-          Eq::two_point_q(fflux, q, qp, dd + 1, d.prm, fl);
+          Eq::two_point_qf(fflux, q, qp, dd + 1, d.prm, fl);
 #pragma unroll
           for (int v = 0; v < NV; ++v) xb[v * NN + n] = fl[v];
           if (NONCONS) {

@@ -474,7 +474,7 @@ static int create_impl(const trixib200_config* cfg, const trixib200_basis_host* 
   }
 
   // ---- physics parameters
-  d.prm.gamma = c.gamma; d.prm.c_h = c.c_h;
+  d.prm.gamma = c.gamma; d.prm.c_h = c.c_h; d.prm.inv_gm1 = 1.0 / (c.gamma - 1.0);
   for (int q = 0; q < 3; ++q) d.prm.a[q] = c.advection_velocity[q];
   d.volume_integral = c.volume_integral; d.vol_flux = c.volume_flux; d.fv_flux = c.volume_flux_fv;
   d.surf_flux = c.surface_flux; d.noncons = c.nonconservative; d.ic = c.initial_condition; d.src = c.source_terms;
