@@ -76,14 +76,19 @@ def test_stages_match_oracle(name):
         assert np.abs(semi.cache("alpha") - o.f64("alpha")).max() <= 1e-12
 
 
-@pytest.mark.parametrize("staged_only", [True, False], ids=["staged", "fused"])
+@pytest.mark.parametrize("kernel", ["staged", "fused", "fused_node"])
 @pytest.mark.parametrize("name", sorted(CASES))
-def test_rhs_matches_oracle(name, staged_only):
-    """Whole rhs!: du within 1e-12 (relative max-norm) of the CPU reference after one call."""
+def test_rhs_matches_oracle(name, kernel):
+    """Whole rhs!: du within 1e-12 (relative max-norm) of the CPU reference after one call, for every kernel
+    family: staged (materialising), fused (best available: warp-per-element in 3D FD) and fused_node
+    (thread-per-node fused kernel forced)."""
     c = CASES[name]
-    o, semi = make_oracle(c), make_semi(c, staged_only=staged_only)
-    if not staged_only and not semi.fused:
-        pytest.skip("fused path covers polydeg 3 in 2D/3D; this case runs the staged kernels")
+    o = make_oracle(c)
+    semi = make_semi(c, staged_only=(kernel == "staged"), no_warp_kernel=(kernel == "fused_node"))
+    if kernel != "staged" and not semi.fused:
+        pytest.skip("fused kernels cover polydeg 3 in 2D/3D; this case runs the staged kernels")
+    if kernel == "fused_node" and not make_semi(c).warp3d:
+        pytest.skip("the default fused kernel already is the thread-per-node one here")
     for t0 in (0.0, 0.37):
         u = o.compute_coefficients(t0)
         du_ref = o.rhs(u, t0)
@@ -101,7 +106,8 @@ def test_fused_equals_staged_on_random_state(name):
     with the oracle."""
     c = CASES[name]
     o, fused, staged = make_oracle(c), make_semi(c), make_semi(c, staged_only=True)
-    assert fused.fused and not staged.fused
+    fused_node = make_semi(c, no_warp_kernel=True)
+    assert fused.fused and not staged.fused and not fused_node.warp3d
     rng = np.random.default_rng(7)
     u = o.compute_coefficients(0.0)
     nv = o.nvars
@@ -113,12 +119,12 @@ def test_fused_equals_staged_on_random_state(name):
     u = uu.ravel()
     du_ref = o.rhs(u, 0.0)
     outs = []
-    for semi in (fused, staged):
+    for semi in (fused, staged, fused_node):
         u_d, du_d = _to_dev(semi, u), semi.new_vector()
         semi.rhs(du_d, u_d, 0.0)
         outs.append(du_d.cpu().numpy())
         assert rel_max_err(outs[-1], du_ref) <= TOL
-    assert rel_max_err(outs[0], outs[1]) <= TOL
+    assert rel_max_err(outs[0], outs[1]) <= TOL and rel_max_err(outs[2], outs[1]) <= TOL
 
 
 @pytest.mark.parametrize("name", sorted(CASES))

@@ -6,13 +6,14 @@ import torch, numpy as np
 import cases
 
 levels = [int(a) for a in sys.argv[1:]] or [4, 5, 6]
-for staged in (False, True):
+kern = os.environ.get("KERN", "auto")
+for staged in (False,):
     for lv in levels:
         if staged and lv > 6:
             continue
         c = dict(cases.CASES["c5_euler_ec_3d"], level=lv)
         t0 = time.time()
-        semi = cases.make_semi(c, staged_only=staged, node_coordinates=False)
+        semi = cases.make_semi(c, staged_only=(kern == "staged"), no_warp_kernel=(kern == "node"), node_coordinates=False)
         t1 = time.time()
         u = semi.compute_coefficients_gpu(0.0, on_device=True)
         du = semi.new_vector()
@@ -22,7 +23,7 @@ for staged in (False, True):
         reps = 20
         ms = semi.time_rhs(du, u, 0.0, reps) / reps
         nd = semi.ndofs()
-        print(f"level {lv} staged={staged} E={semi.nelements} setup {t1-t0:.1f}s rhs {ms:.4f} ms  "
+        print(f"level {lv} kern={kern} warp3d={semi.warp3d} E={semi.nelements} setup {t1-t0:.1f}s rhs {ms:.4f} ms  "
               f"{nd/ms/1e6:.2f} GDOF/s  algo-HBM {81*nd/ms/1e6:.0f} GB/s", flush=True)
         del semi, u, du
         torch.cuda.empty_cache()

@@ -107,8 +107,11 @@ k_fused(Dev d, double* __restrict__ du, const double* __restrict__ u, double t, 
 #pragma unroll
       for (int v = 0; v < NV; ++v) qo[v] = sq[v * NN + own];
       Eq::to_qf(nb, d.prm, qn);
-      if (side) Eq::two_point_qf(sflux, qo, qn, dim + 1, d.prm, fl);
-      else Eq::two_point_qf(sflux, qn, qo, dim + 1, d.prm, fl);
+      // order (ll, rr) by selects, not by a branch: both neighbours then evaluate bitwise the same flux
+      double qa[NV], qb[NV];
+#pragma unroll
+      for (int v = 0; v < NV; ++v) { qa[v] = side ? qo[v] : qn[v]; qb[v] = side ? qn[v] : qo[v]; }
+      Eq::two_point_qf(sflux, qa, qb, dim + 1, d.prm, fl);
       if (NONCONS) {
         double g[NV];
         Eq::noncons_q(qo, qn, dim + 1, d.prm, g);
@@ -163,9 +166,9 @@ k_fused(Dev d, double* __restrict__ du, const double* __restrict__ u, double t, 
         double qp[NV], f[NV];
 #pragma unroll
         for (int v = 0; v < NV; ++v) qp[v] = sq[v * NN + np];
-        // lower node first, like Trixi's flux_differencing_kernel! (i, ii > i)
-        if (pc > ic) Eq::two_point_qf(vflux, q, qp, dc + 1, d.prm, f);
-        else Eq::two_point_qf(vflux, qp, q, dc + 1, d.prm, f);
+        // symmetric two-point flux: argument order is immaterial up to rounding, and both nodes of the pair use
+        // this one value (a per-lane order branch would make the warp evaluate the flux twice)
+        Eq::two_point_qf(vflux, q, qp, dc + 1, d.prm, f);
         const double w = scale * op.Dsplit[ic + N * pc];
 #pragma unroll
         for (int v = 0; v < NV; ++v) { xb[v * NN + n] = f[v]; acc[v] += w * f[v]; }

@@ -8,12 +8,14 @@
 #include <cmath>
 #include <cstdio>
 #include <cstring>
+#include <cstdint>
 #include <string>
 #include <vector>
 #include "../../include/trixib200.h"
 #include "device.cuh"
 #include "kernels_staged.cuh"
 #include "kernels_fused.cuh"
+#include "kernels_warp3d.cuh"
 
 using namespace tb;
 
@@ -232,7 +234,7 @@ struct trixib200_handle {
   std::vector<void*> allocs;
   double* d_scalar = nullptr;
   int64_t launches = 0;
-  bool fused = false;
+  bool fused = false, warp3d = false;
   // fused-path element lists (multi-GPU overlap): interior first, then elements touching a halo face
   int* d_elems_interior = nullptr; int* d_elems_halo = nullptr;
   int64_t n_interior = 0, n_halo_elems = 0;
@@ -484,6 +486,7 @@ static int create_impl(const trixib200_config* cfg, const trixib200_basis_host* 
 
   // ---- fused path availability (3D/2D, polydeg 3) and its element lists
   h->fused = !(c.flags & TRIXIB200_FLAG_STAGED_ONLY) && fused_available(c);
+  h->warp3d = h->fused && !(c.flags & TRIXIB200_FLAG_NO_WARP_KERNEL) && warp3d_available(c);
   {
     int* p;
     if (int rc = upload(h, P.face_nbr, &p)) return rc;
@@ -537,6 +540,7 @@ extern "C" int64_t trixib200_size(const trixib200_handle* h, const char* name) {
   if (n == "nmortars") return d.M;
   if (n == "nhalo_faces") return d.nhalo_recv;
   if (n == "fused") return h->fused ? 1 : 0;
+  if (n == "warp3d") return h->warp3d ? 1 : 0;
   if (n == "npeers") return (int64_t)h->peers.size();
   return -1;
 }
@@ -666,19 +670,22 @@ static int rhs_fused(trixib200_handle* h, double* du, const double* u, double t)
   if (d.B > 0) { st_prolong_boundaries(h, u); st_boundary_flux(h, t); }
   if (d.M > 0) { st_prolong_mortars(h, u); st_mortar_flux(h); }
   bool multi = h->cfg.nranks > 1 && d.nhalo_send > 0;
-  if (!multi) {
-    if (int rc = fused_launch(h->cfg, d, du, u, t, nullptr, d.E, h->stream, h->sm_count)) return fail(rc, "fused launch failed");
+  // warp-per-element kernel (3D flux differencing, polydeg 3) when its 16-byte copies are aligned
+  const bool w3 = h->warp3d && ((((uintptr_t)u) | ((uintptr_t)du)) & 15) == 0;
+  auto launch = [&](const int* elems, int64_t count) -> int {
+    if (count <= 0) return 0;
+    int rc = w3 ? warp3d_launch(h->cfg, d, du, u, t, elems, count, h->stream, h->sm_count)
+                : fused_launch(h->cfg, d, du, u, t, elems, count, h->stream, h->sm_count);
+    if (rc) return fail(rc, "fused launch failed");
     h->launches++;
+    return 0;
+  };
+  if (!multi) {
+    if (int rc = launch(nullptr, d.E)) return rc;
   } else {
-    if (h->n_interior > 0) {
-      if (int rc = fused_launch(h->cfg, d, du, u, t, h->d_elems_interior, h->n_interior, h->stream, h->sm_count)) return fail(rc, "fused launch failed");
-      h->launches++;
-    }
+    if (int rc = launch(h->d_elems_interior, h->n_interior)) return rc;
     if (int rc = halo_wait(h)) return rc;
-    if (h->n_halo_elems > 0) {
-      if (int rc = fused_launch(h->cfg, d, du, u, t, h->d_elems_halo, h->n_halo_elems, h->stream, h->sm_count)) return fail(rc, "fused launch failed");
-      h->launches++;
-    }
+    if (int rc = launch(h->d_elems_halo, h->n_halo_elems)) return rc;
   }
   return 0;
 }

@@ -27,7 +27,7 @@ def _torch():
 
 class SemidiscretizationHyperbolicGPU:
     def __init__(self, mesh: TreeMesh, equations, initial_condition, solver, source_terms=None,
-                 boundary_conditions=boundary_condition_periodic, staged_only=False, device=None,
+                 boundary_conditions=boundary_condition_periodic, staged_only=False, no_warp_kernel=False, device=None,
                  rank=0, nranks=1, comm_id=None, node_coordinates="auto"):
         if mesh.ndim != equations.ndim:
             raise ValueError("mesh and equations have different dimensions")
@@ -40,7 +40,7 @@ class SemidiscretizationHyperbolicGPU:
         self.device_index = torch.cuda.current_device() if device is None else int(device)
         self.device = torch.device("cuda", self.device_index)
         self.cache_cpu = init_containers(mesh, solver.basis.nodes)   # what Trixi's init_* give the Julia shim
-        self._create(staged_only, comm_id, node_coordinates)
+        self._create(staged_only, comm_id, node_coordinates, no_warp_kernel)
 
     # ------------------------------------------------------------------ handle construction
     def _config(self, staged_only):
@@ -130,9 +130,11 @@ class SemidiscretizationHyperbolicGPU:
         mh.mortars_orientations = i64(c.mortars.orientations)
         return bh, mh, keep
 
-    def _create(self, staged_only, comm_id, node_coordinates):
+    def _create(self, staged_only, comm_id, node_coordinates, no_warp_kernel=False):
         L = _lib.lib()
         cfg = self._config(staged_only)
+        if no_warp_kernel:
+            cfg.flags |= _lib.FLAG_NO_WARP_KERNEL
         bh, mh, keep = self._host_structs(node_coordinates)
         h = C.c_void_p()
         _lib.check(L.trixib200_create(C.byref(cfg), C.byref(bh), C.byref(mh), C.byref(h)))
@@ -146,6 +148,7 @@ class SemidiscretizationHyperbolicGPU:
         self.nelements, self.first_element = self.size("nelements"), self.size("first_element")
         self.nelements_global = self.size("nelements_global")
         self.fused = bool(self.size("fused"))
+        self.warp3d = bool(self.size("warp3d"))
         self._stream = None
 
     def __del__(self):
