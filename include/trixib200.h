@@ -128,6 +128,15 @@ int64_t trixib200_size(const trixib200_handle* h, const char* name);
  * handle's stream; du is fully overwritten. */
 int trixib200_rhs(trixib200_handle* h, double* du, const double* u, double t);
 
+/* Same operation on HOST vectors (length nunknowns): host->device copy of u, rhs!, device->host copy of du on
+ * the handle's streams, synchronous. This is the entry point for callers whose state lives in host memory
+ * (Trixi's CPU `rhs!(du_ode, u_ode, semi, t)` signature); the transfers are pipelined over element chunks so
+ * that upload, kernels and download overlap. Host buffers should be page-locked (trixib200_host_register). */
+int trixib200_rhs_host(trixib200_handle* h, double* du_host, const double* u_host, double t);
+/* page-lock / unlock a caller-owned host buffer of n doubles (cudaHostRegister) */
+int trixib200_host_register(trixib200_handle* h, double* host, int64_t n);
+int trixib200_host_unregister(trixib200_handle* h, double* host);
+
 /* replaces: max_dt(u, t, mesh, constant_speed, equations, dg, cache) (reference
  * src/callbacks_step/stepsize_dg_3d.jl:1-45). Device reduction (+ allreduce-max over ranks); synchronises. */
 int trixib200_max_dt(trixib200_handle* h, const double* u, double t, double* out_host);

@@ -1,0 +1,169 @@
+"""CPU tests of the host logic of the product: the numpy TreeMesh / container builder and LGL basis (what the
+Julia shim would get from Trixi.jl) against the oracle's independent C++ pointer-tree implementation
+(connectivity bit-exact), and the Morton-range partition plan (trixib200_plan_*, host only), including a
+world_size-2 gloo run that exchanges halo face traces exactly as the NCCL path does."""
+import os
+import subprocess
+import sys
+
+import numpy as np
+import pytest
+
+import cases
+from cases import CASES, make_oracle
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+MESHES = {
+    "uniform_1d": dict(ndim=1, level=4), "uniform_2d": dict(ndim=2, level=3), "uniform_3d": dict(ndim=3, level=2),
+    "box_2d": dict(ndim=2, level=2, patches=cases.BOX2), "box_3d": dict(ndim=3, level=2, patches=cases.BOX3),
+    "box_3d_l3": dict(ndim=3, level=3, patches=cases.BOX3),
+    "nonperiodic_2d": dict(ndim=2, level=3, periodic=False), "nonperiodic_3d": dict(ndim=3, level=2, periodic=False),
+    "nonperiodic_box_3d": dict(ndim=3, level=2, periodic=False, patches=cases.BOX3),
+    "two_patches_2d": dict(ndim=2, level=2, patches=cases.BOX2 + (dict(type="box", coordinates_min=(0.25, -0.5),
+                                                                       coordinates_max=(0.75, 0.5)),)),
+}
+
+
+def _build(m, polydeg=3):
+    import trixib200 as T
+    nd = m["ndim"]
+    periodic = m.get("periodic", True)
+    mesh = T.TreeMesh((-1.0,) * nd, (1.0,) * nd, initial_refinement_level=m["level"],
+                      refinement_patches=m.get("patches", ()), periodicity=periodic)
+    basis = T.LobattoLegendreBasisGPU(polydeg)
+    c = T.init_containers(mesh, basis.nodes)
+    o = make_oracle(cases.case(nd, "advection", level=m["level"], polydeg=polydeg, patches=m.get("patches", ()),
+                               periodic=periodic, bc="periodic" if periodic else "dirichlet_ic"))
+    return mesh, basis, c, o
+
+
+@pytest.mark.parametrize("name", sorted(MESHES))
+def test_containers_bit_exact_vs_oracle(name):
+    mesh, basis, c, o = _build(MESHES[name])
+    assert c.elements.inverse_jacobian.shape[0] == o.nelements
+    assert np.array_equal(c.elements.inverse_jacobian, o.f64("inverse_jacobian"))
+    assert np.array_equal(c.elements.node_coordinates.ravel(order="F"), o.f64("node_coordinates"))
+    assert np.array_equal(c.interfaces.neighbor_ids.ravel(order="F"), o.i64("interfaces.neighbor_ids"))
+    assert np.array_equal(c.interfaces.orientations, o.i64("interfaces.orientations"))
+    assert np.array_equal(c.boundaries.neighbor_ids, o.i64("boundaries.neighbor_ids"))
+    assert np.array_equal(c.boundaries.orientations, o.i64("boundaries.orientations"))
+    assert np.array_equal(c.boundaries.neighbor_sides, o.i64("boundaries.neighbor_sides"))
+    assert np.array_equal(c.boundaries.n_boundaries_per_direction, o.i64("boundaries.n_boundaries_per_direction"))
+    assert np.array_equal(c.boundaries.node_coordinates.ravel(order="F"), o.f64("boundaries.node_coordinates"))
+    assert np.array_equal(c.mortars.neighbor_ids.ravel(order="F"), o.i64("mortars.neighbor_ids"))
+    assert np.array_equal(c.mortars.large_sides, o.i64("mortars.large_sides"))
+    assert np.array_equal(c.mortars.orientations, o.i64("mortars.orientations"))
+
+
+def test_known_counts():
+    """SURVEY.md section 8 sizes: periodic uniform meshes have I = d * E; config 4 has 120 elements, 24 mortars."""
+    _, _, c, _ = _build(MESHES["uniform_3d"])
+    assert c.interfaces.orientations.shape[0] == 3 * 64 and c.boundaries.neighbor_ids.shape[0] == 0
+    _, _, c, _ = _build(MESHES["box_3d"])
+    assert c.elements.inverse_jacobian.shape[0] == 120 and c.mortars.orientations.shape[0] == 24
+    _, _, c, _ = _build(MESHES["nonperiodic_3d"])
+    assert c.boundaries.neighbor_ids.shape[0] == 6 * 16
+    assert list(c.boundaries.n_boundaries_per_direction) == [16] * 6
+
+
+@pytest.mark.parametrize("polydeg", [1, 2, 3, 4, 5, 7])
+def test_basis_matches_oracle(polydeg):
+    import trixib200 as T
+    b = T.LobattoLegendreBasisGPU(polydeg)
+    m = T.MortarL2GPU(b)
+    o = make_oracle(cases.case(1, "advection", level=1, polydeg=polydeg))
+    from trixib200._lib import colmajor
+    for name, val in (("nodes", b.nodes), ("weights", b.weights), ("inverse_weights", b.inverse_weights)):
+        assert np.abs(val - o.f64(name)).max() <= 4e-16 * max(1.0, np.abs(val).max()), name
+    for name, val in (("derivative_dhat", b.derivative_dhat), ("derivative_split", b.derivative_split),
+                      ("boundary_interpolation", b.boundary_interpolation),
+                      ("inverse_vandermonde_legendre", b.inverse_vandermonde_legendre),
+                      ("forward_upper", m.forward_upper), ("forward_lower", m.forward_lower),
+                      ("reverse_upper", m.reverse_upper), ("reverse_lower", m.reverse_lower)):
+        assert np.abs(colmajor(val) - o.f64(name)).max() <= 2e-14 * max(1.0, np.abs(o.f64(name)).max()), name
+    if polydeg == 3:   # closed forms
+        assert np.allclose(b.nodes, [-1, -np.sqrt(0.2), np.sqrt(0.2), 1], atol=1e-15)
+        assert np.allclose(b.weights, [1 / 6, 5 / 6, 5 / 6, 1 / 6], atol=1e-15)
+        assert abs(b.derivative_split[0, 0]) <= 1e-14 and abs(b.derivative_split[3, 3]) <= 1e-14
+
+
+# ------------------------------------------------------------------------------------------- partition plan
+def _plan(mesh, basis, rank, nranks):
+    from trixib200 import distributed as D
+    return D.partition_plan(mesh, basis.nodes, rank, nranks, bc_periodic=all(mesh.periodicity))
+
+
+@pytest.mark.parametrize("nranks", [1, 2, 3, 4, 8])
+@pytest.mark.parametrize("name", ["uniform_3d", "uniform_2d", "nonperiodic_3d", "uniform_1d"])
+def test_partition_plan_invariants(name, nranks):
+    mesh, basis, c, _ = _build(MESHES[name])
+    E, nd = c.elements.inverse_jacobian.shape[0], mesh.ndim
+    gl = c.interfaces.neighbor_ids
+    plans = [_plan(mesh, basis, r, nranks)[0] for r in range(nranks)]
+    firsts = [p.scalar("first_element") for p in plans]
+    counts = [p.scalar("nelements") for p in plans]
+    assert firsts[0] == 0 and sum(counts) == E and max(counts) - min(counts) <= 1
+    assert all(firsts[r + 1] == firsts[r] + counts[r] for r in range(nranks - 1))
+    seen = np.zeros(gl.shape[1], dtype=int)
+    for r, p in enumerate(plans):
+        first, n = firsts[r], counts[r]
+        ifg, L, R, dim = p.array("if_global"), p.array("if_left"), p.array("if_right"), p.array("if_dim")
+        assert np.array_equal(dim + 1, c.interfaces.orientations[ifg])
+        for s in range(ifg.shape[0]):
+            gL, gR = gl[0, ifg[s]] - 1, gl[1, ifg[s]] - 1
+            if L[s] >= 0:
+                assert L[s] + first == gL
+            if R[s] >= 0:
+                assert R[s] + first == gR
+            assert (L[s] >= 0) == (first <= gL < first + n) and (R[s] >= 0) == (first <= gR < first + n)
+            seen[ifg[s]] += 1
+        # interior + halo element lists partition the local range
+        ei, eh = p.array("elems_interior"), p.array("elems_halo")
+        assert sorted(np.concatenate([ei, eh]).tolist()) == list(range(n))
+        # face neighbour table agrees with the interface list
+        fn = p.array("face_nbr").reshape(n, 2 * nd)
+        for s in range(ifg.shape[0]):
+            if L[s] >= 0:
+                assert fn[L[s], 2 * dim[s] + 1] == R[s]
+            if R[s] >= 0:
+                assert fn[R[s], 2 * dim[s]] == L[s]
+        # send list: peer-major, same global interfaces in the same order on both sides
+        peers, cnt = p.array("peers"), p.array("peer_count")
+        sg = p.array("send_global_iface")
+        off = 0
+        for q, k in zip(peers, cnt):
+            mine = sg[off: off + k]
+            pq = plans[q]
+            qpeers, qcnt, qsg = pq.array("peers"), pq.array("peer_count"), pq.array("send_global_iface")
+            qoff = int(sum(qcnt[: list(qpeers).index(r)]))
+            assert np.array_equal(mine, qsg[qoff: qoff + k])
+            off += k
+        if nranks == 1:
+            assert peers.size == 0 and eh.size == 0
+    # every interface is owned by one rank (both sides local) or by exactly two (halo)
+    assert seen.min() >= 1 and seen.max() <= 2
+
+
+def test_partition_rejects_mortar_across_ranks_and_bad_args():
+    import trixib200 as T
+    mesh, basis, c, _ = _build(MESHES["box_3d"])
+    with pytest.raises(T.TrixiB200Error):
+        _plan(mesh, basis, 0, 2)
+    mesh, basis, c, _ = _build(MESHES["uniform_3d"])
+    with pytest.raises(T.TrixiB200Error):
+        _plan(mesh, basis, 2, 2)
+    with pytest.raises(T.TrixiB200Error):
+        _plan(mesh, basis, 0, 65)      # fewer elements than ranks
+
+
+def test_halo_exchange_world_size_2_gloo():
+    """Two processes (gloo) each build their plan, pack the face traces the plan lists, exchange them with
+    send/recv in peer order, and check the received halo slots against the oracle's interfaces.u."""
+    env = dict(os.environ, MASTER_ADDR="127.0.0.1", MASTER_PORT="29611", OMP_NUM_THREADS="1")
+    res = subprocess.run([sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node=2",
+                          "--master-addr", "127.0.0.1", "--master-port", "29611",
+                          os.path.join(ROOT, "tests", "halo_gloo_worker.py")], env=env, capture_output=True, text=True,
+                         timeout=600)
+    assert res.returncode == 0, res.stdout[-3000:] + res.stderr[-3000:]
+    assert res.stdout.count("HALO_OK") == 2, res.stdout[-2000:]

@@ -1,0 +1,229 @@
+"""CPU tests that pin the oracle (oracle/, the C++ restatement of Trixi.jl's CPU DGSEM rhs!):
+
+ * against Trixi.jl's own published regression norms of the elixirs that are the reference's examples
+   (tests/golden/trixi_regression_norms.json) -- full runs: rhs!, CK2N54, StepsizeCallback, analysis norms;
+ * against the committed golden rhs! fixtures (tests/golden/rhs_*.npz, made by tests/golden/make_golden.py);
+ * through structural invariants that need no external truth: flux consistency/symmetry, free-stream
+   preservation, discrete conservation, entropy conservation of the EC scheme, experimental order of convergence.
+"""
+import json
+import os
+
+import numpy as np
+import pytest
+
+import oracle as O
+import cases
+from cases import CASES, make_oracle, rel_max_err
+
+GOLDEN_DIR = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
+NORMS = json.load(open(os.path.join(GOLDEN_DIR, "trixi_regression_norms.json")))["cases"]
+
+
+def _oracle_for(entry):
+    nd = entry["ndim"]
+    kw = dict(ndim=nd, equations=entry["equations"], polydeg=3, initial_refinement_level=entry["level"])
+    if entry["equations"] == "advection":
+        kw.update(advection_velocity=tuple(entry["advection_velocity"]), coordinates_min=(-1.0,) * 3,
+                  coordinates_max=(1.0,) * 3)
+    else:
+        kw.update(volume_integral="flux_differencing", volume_flux="flux_ranocha", surface_flux="flux_ranocha",
+                  initial_condition="weak_blast_wave", coordinates_min=(-2.0,) * 3, coordinates_max=(2.0,) * 3)
+    return O.Oracle(**kw)
+
+
+@pytest.mark.parametrize("name", sorted(n for n, e in NORMS.items() if e.get("gate", True)))
+def test_oracle_reproduces_trixi_published_norms(name):
+    e = NORMS[name]
+    o = _oracle_for(e)
+    u, _ = o.solve(o.compute_coefficients(0.0), 0.0, e["tend"], cfl=e["cfl"])
+    l2, linf = o.error_norms(u, e["tend"])
+    assert np.abs(l2 - np.array(e["l2"])).max() <= 1e-12, (l2.tolist(), e["l2"])
+    if e["linf"] is not None:
+        assert np.abs(linf - np.array(e["linf"])).max() <= 1e-11, (linf.tolist(), e["linf"])
+
+
+def test_ungated_recalled_norms_are_close():
+    """Low-confidence recalled digits are only required to agree to 2 %, documenting the gap (see the JSON note)."""
+    e = NORMS["euler_ec_3d"]
+    o = _oracle_for(e)
+    u, _ = o.solve(o.compute_coefficients(0.0), 0.0, e["tend"], cfl=e["cfl"])
+    l2, _ = o.error_norms(u, e["tend"])
+    assert np.abs(l2 / np.array(e["l2"]) - 1).max() <= 0.02
+
+
+def _golden_names():
+    return sorted(f[4:-4] for f in os.listdir(GOLDEN_DIR) if f.startswith("rhs_") and f.endswith(".npz"))
+
+
+@pytest.mark.parametrize("name", _golden_names())
+def test_oracle_reproduces_golden_fixtures(name):
+    import sys
+    sys.path.insert(0, GOLDEN_DIR)
+    import make_golden
+    g = np.load(os.path.join(GOLDEN_DIR, f"rhs_{name}.npz"))
+    new = make_golden.generate(name)
+    for k in g.files:
+        if g[k].dtype.kind == "i":
+            assert np.array_equal(g[k], new[k]), k           # connectivity: bit-exact
+        else:
+            assert rel_max_err(new[k], g[k]) <= 1e-14, k
+
+
+# ------------------------------------------------------------------------------------------- flux properties
+def _euler_state(rng, nd):
+    rho = rng.uniform(0.5, 2.0)
+    v = rng.uniform(-1, 1, nd)
+    p = rng.uniform(0.5, 2.0)
+    return np.concatenate([[rho], rho * v, [p / 0.4 + 0.5 * rho * (v @ v)]])
+
+
+def _euler_flux(u, o, nd, gamma=1.4):
+    rho, m, e = u[0], u[1:1 + nd], u[-1]
+    v = m / rho
+    p = (gamma - 1) * (e - 0.5 * rho * (v @ v))
+    f = np.empty_like(u)
+    f[0] = m[o - 1]
+    f[1:1 + nd] = m * v[o - 1]
+    f[o] += p
+    f[-1] = (e + p) * v[o - 1]
+    return f
+
+
+@pytest.mark.parametrize("nd", [1, 2, 3])
+@pytest.mark.parametrize("flux", ["flux_central", "flux_lax_friedrichs", "flux_lax_friedrichs_naive", "flux_hll",
+                                  "flux_hll_naive", "flux_ranocha", "flux_shima_etal"])
+def test_euler_two_point_fluxes_consistent_and_symmetric(nd, flux):
+    rng = np.random.default_rng(nd * 100 + len(flux))
+    for _ in range(20):
+        ul, ur = _euler_state(rng, nd), _euler_state(rng, nd)
+        for o in range(1, nd + 1):
+            f = O.two_point_flux("euler", nd, flux, ul, ul, o)
+            assert np.abs(f - _euler_flux(ul, o, nd)).max() <= 1e-13 * max(1, np.abs(f).max())
+            if flux in ("flux_central", "flux_ranocha", "flux_shima_etal"):
+                a = O.two_point_flux("euler", nd, flux, ul, ur, o)
+                b = O.two_point_flux("euler", nd, flux, ur, ul, o)
+                assert np.abs(a - b).max() <= 1e-14 * max(1, np.abs(a).max())
+
+
+def test_ranocha_flux_is_entropy_conservative():
+    """Tadmor's condition (w_r - w_l) . f* = psi_r - psi_l with psi = rho v_o for the Euler entropy S = -rho s/(g-1)."""
+    rng = np.random.default_rng(3)
+    g = 1.4
+
+    def entropy_vars(u):
+        rho, v, e = u[0], u[1:4] / u[0], u[4]
+        p = (g - 1) * (e - 0.5 * rho * (v @ v))
+        s = np.log(p) - g * np.log(rho)
+        return np.concatenate([[(g - s) / (g - 1) - 0.5 * rho / p * (v @ v)], rho / p * v, [-rho / p]])
+
+    for _ in range(50):
+        ul, ur = _euler_state(rng, 3), _euler_state(rng, 3)
+        if rng.uniform() < 0.5:            # nearly equal states exercise the Taylor branch of ln_mean
+            ur = ul * (1 + 1e-3 * rng.uniform(-1, 1, 5))
+        for o in (1, 2, 3):
+            f = O.two_point_flux("euler", 3, "flux_ranocha", ul, ur, o)
+            lhs = (entropy_vars(ur) - entropy_vars(ul)) @ f
+            rhs = ur[o] - ul[o]
+            assert abs(lhs - rhs) <= 1e-12 * max(1.0, abs(rhs), np.abs(f).max())
+
+
+@pytest.mark.parametrize("flux", ["flux_hindenlang_gassner", "flux_lax_friedrichs", "flux_hlle", "flux_central"])
+def test_mhd_fluxes_consistent(flux):
+    rng = np.random.default_rng(11)
+    g = 5 / 3
+    for _ in range(10):
+        rho, v, B, p, psi = rng.uniform(0.5, 2), rng.uniform(-1, 1, 3), rng.uniform(-1, 1, 3), rng.uniform(0.5, 2), 0.1
+        u = np.concatenate([[rho], rho * v, [p / (g - 1) + 0.5 * rho * (v @ v) + 0.5 * (B @ B) + 0.5 * psi ** 2], B,
+                            [psi]])
+        for o in (1, 2, 3):
+            a = O.two_point_flux("mhd", 3, flux, u, u, o, gamma=g, c_h=1.3)
+            b = O.two_point_flux("mhd", 3, "flux_central", u, u, o, gamma=g, c_h=1.3)
+            assert np.abs(a - b).max() <= 1e-13 * max(1, np.abs(b).max())
+
+
+# ------------------------------------------------------------------------------------------- scheme invariants
+@pytest.mark.parametrize("name", ["c5_euler_ec_3d", "c2_euler_ec_2d", "c3_euler_sc_3d", "euler_mortar_3d",
+                                  "c4_mhd_alfven_mortar_3d", "advection_mortar_3d", "euler_ec_mortar_2d"])
+def test_free_stream_preservation(name):
+    c = dict(CASES[name], ic="constant", source="none")
+    o = make_oracle(c)
+    u = o.compute_coefficients(0.0)
+    du = o.rhs(u, 0.0)
+    assert np.abs(du).max() <= 1e-12 * max(1.0, np.abs(u).max()) * o.f64("inverse_jacobian").max()
+
+
+@pytest.mark.parametrize("name", ["c5_euler_ec_3d", "c2_euler_ec_2d", "c3_euler_sc_3d", "euler_ec_mortar_2d",
+                                  "euler_shock_mortar_3d", "advection_mortar_3d", "euler_ec_1d"])
+def test_discrete_conservation(name):
+    """sum_e J_e sum_n w_n du = 0 on periodic meshes, also across mortars."""
+    c = CASES[name]
+    o = make_oracle(c)
+    u = o.compute_coefficients(0.0)
+    du = o.rhs(u, 0.0)
+    tot, scale = o.integrate(du), o.integrate(np.abs(du))
+    assert np.abs(tot / np.maximum(scale, 1e-300)).max() <= 1e-12
+
+
+@pytest.mark.parametrize("name", ["c5_euler_ec_3d", "c2_euler_ec_2d", "euler_ec_1d"])
+def test_entropy_conservation(name):
+    """flux_ranocha volume + surface flux on a conforming periodic mesh: dS/dt = sum w(u) . du = 0 to round-off."""
+    o = make_oracle(CASES[name])
+    u = o.compute_coefficients(0.0)
+    du = o.rhs(u, 0.0)
+    rate = o.entropy_rate(du, u)
+    scale = o.integrate(np.abs(du)).max()
+    assert abs(rate) <= 1e-12 * max(scale, 1.0)
+
+
+def test_shock_capturing_dissipates_entropy():
+    c = dict(CASES["c3_euler_sc_3d"], volume_flux_fv="flux_lax_friedrichs", surface_flux="flux_lax_friedrichs")
+    o = make_oracle(c)
+    u = o.compute_coefficients(0.0)
+    assert o.entropy_rate(o.rhs(u, 0.0), u) < 0
+    alpha = o.indicator(u)
+    assert alpha.max() <= 0.5 + 1e-15 and alpha.min() >= 0.0 and alpha.max() > 0.0
+
+
+@pytest.mark.parametrize("nd,eq", [(1, "advection"), (2, "advection"), (2, "euler"), (3, "euler")])
+def test_experimental_order_of_convergence(nd, eq):
+    """EOC ~ polydeg + 1 = 4 (manufactured solution with source_terms_convergence_test for Euler)."""
+    errs = []
+    levels = (3, 4)   # level 2 is pre-asymptotic in 3D (4 elements per wavelength)
+    for lv in levels:
+        kw = dict(ndim=nd, equations=eq, polydeg=3, initial_refinement_level=lv)
+        if eq == "euler":
+            kw.update(source="convergence_test", coordinates_min=(0.0,) * 3, coordinates_max=(2.0,) * 3)
+        o = O.Oracle(**kw)
+        tend = 0.2
+        u, _ = o.solve(o.compute_coefficients(0.0), 0.0, tend, cfl=0.5)
+        errs.append(o.error_norms(u, tend)[0][0])
+    eoc = np.log2(errs[0] / errs[1])
+    assert 3.5 <= eoc <= 5.0, (errs, eoc)
+
+
+def test_coordinate_permutation_symmetry_3d():
+    """Swapping x and y in the initial state (and the momentum components) permutes du the same way: catches
+    direction-specific indexing errors that 1D/2D published norms cannot see."""
+    o = make_oracle(CASES["c5_euler_ec_3d"])
+    E, n, nv = o.nelements, 4, 5
+    x = o.f64("node_coordinates").reshape(E, n, n, n, 3)
+    rng = np.random.default_rng(5)
+    # smooth asymmetric field evaluated at the nodes
+    def state(xx):
+        rho = 1.0 + 0.2 * np.sin(np.pi * (0.5 * xx[..., 0] + 0.25 * xx[..., 1])) * np.cos(np.pi * 0.5 * xx[..., 2])
+        v = np.stack([0.3 * np.sin(np.pi * 0.5 * xx[..., 1]), -0.2 * np.cos(np.pi * 0.5 * xx[..., 0]),
+                      0.1 * np.sin(np.pi * 0.5 * (xx[..., 0] + xx[..., 2]))], -1)
+        p = 1.0 + 0.1 * np.cos(np.pi * 0.5 * (xx[..., 0] - xx[..., 1]))
+        return np.concatenate([rho[..., None], rho[..., None] * v, (p / 0.4 + 0.5 * rho * (v * v).sum(-1))[..., None]], -1)
+    u1 = state(x)
+    xs = x[..., [1, 0, 2]]
+    u2 = state(xs)[..., [0, 2, 1, 3, 4]]
+    du1 = o.rhs(np.ascontiguousarray(u1).ravel(), 0.0).reshape(E, n, n, n, nv)
+    du2 = o.rhs(np.ascontiguousarray(u2).ravel(), 0.0).reshape(E, n, n, n, nv)
+    # map: element at centre (cx,cy,cz) <-> (cy,cx,cz); node (k,j,i) <-> (k,i,j)
+    cen = o.f64("cell_centers").reshape(E, 3)
+    key = {tuple(np.round(c, 9)): e for e, c in enumerate(cen)}
+    perm = np.array([key[tuple(np.round(c[[1, 0, 2]], 9))] for c in cen])
+    du2m = du2[perm].transpose(0, 1, 3, 2, 4)[..., [0, 2, 1, 3, 4]]
+    assert rel_max_err(du2m, du1) <= 1e-13

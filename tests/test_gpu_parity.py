@@ -215,3 +215,67 @@ def test_unsupported_combinations_raise():
     c = dict(CASES["advection_basic_3d"], surface_flux="flux_ranocha")
     with pytest.raises(T.TrixiB200Error):
         make_semi(c)
+
+
+# ------------------------------------------------------------------------------------------- golden fixtures
+import os as _os
+
+_GOLDEN = _os.path.join(_os.path.dirname(_os.path.abspath(__file__)), "golden")
+_GOLDEN_CASES = {"c1_advection_1d": None, "c2_euler_ec_2d": 2, "c3_euler_sc_3d": 2, "c4_mhd_alfven_mortar_3d": None,
+                 "c5_euler_ec_3d": 2, "euler_nonperiodic_2d": 2, "euler_ec_mortar_2d": 2}
+
+
+@pytest.mark.parametrize("kernel", ["staged", "fused"])
+@pytest.mark.parametrize("name", sorted(_GOLDEN_CASES))
+def test_rhs_matches_committed_golden(name, kernel):
+    """libtrixib200 against the committed fixtures (tests/golden/rhs_*.npz: u, du after one rhs!, max_dt and the
+    connectivity, generated by tests/golden/make_golden.py) -- independent of the oracle binary on this box."""
+    g = np.load(_os.path.join(_GOLDEN, f"rhs_{name}.npz"))
+    c = CASES[name]
+    semi = make_semi(c, level=_GOLDEN_CASES[name], staged_only=(kernel == "staged"))
+    cc = semi.cache_cpu
+    assert np.array_equal(cc.interfaces.neighbor_ids.ravel(order="F"), g["interfaces__neighbor_ids"])
+    assert np.array_equal(cc.interfaces.orientations, g["interfaces__orientations"])
+    assert np.array_equal(cc.boundaries.neighbor_ids, g["boundaries__neighbor_ids"])
+    assert np.array_equal(cc.mortars.neighbor_ids.ravel(order="F"), g["mortars__neighbor_ids"])
+    assert np.array_equal(cc.mortars.large_sides, g["mortars__large_sides"])
+    u_d, du_d = _to_dev(semi, g["u"]), semi.new_vector().fill_(float("nan"))
+    semi.rhs(du_d, u_d, float(g["t"][0]))
+    assert rel_max_err(du_d.cpu().numpy(), g["du"]) <= TOL
+    assert abs(semi.max_dt(u_d, 0.0) - g["max_dt"][0]) <= 1e-13 * g["max_dt"][0]
+
+
+@pytest.mark.parametrize("name", ["c5_euler_ec_3d", "c3_euler_sc_3d", "c4_mhd_alfven_mortar_3d", "c1_advection_1d"])
+def test_rhs_host_matches_device_path(name):
+    """trixib200_rhs_host (host vectors in / out, transfers inside the library) == rhs! on resident vectors."""
+    torch = _torch()
+    c = CASES[name]
+    o, semi = make_oracle(c), make_semi(c)
+    u = o.compute_coefficients(0.0)
+    du_ref = o.rhs(u, 0.2)
+    u_h = torch.from_numpy(u).pin_memory()
+    du_h = torch.full_like(u_h, float("nan")).pin_memory()
+    semi.rhs_host(du_h, u_h, 0.2)
+    assert rel_max_err(du_h.numpy(), du_ref) <= TOL
+    du_np = np.full_like(u, np.nan)          # pageable numpy buffers work too
+    semi.rhs_host(du_np, u, 0.2)
+    assert np.array_equal(du_np, du_h.numpy())
+    u_d, du_d = _to_dev(semi, u), semi.new_vector()
+    semi.rhs(du_d, u_d, 0.2)
+    assert np.array_equal(du_d.cpu().numpy(), du_np)
+
+
+@pytest.mark.parametrize("nranks", [2, 4, 8])
+def test_multi_gpu_rhs_matches_oracle(nranks):
+    """Morton-curve partition over `nranks` GPUs of this box (one process per GPU, NCCL halo exchange)."""
+    import subprocess, sys
+    torch = _torch()
+    if torch.cuda.device_count() < nranks:
+        pytest.skip(f"needs {nranks} GPUs")
+    here = _os.path.dirname(_os.path.abspath(__file__))
+    port = 29700 + nranks
+    res = subprocess.run([sys.executable, "-m", "torch.distributed.run", "--nnodes=1", f"--nproc-per-node={nranks}",
+                          "--master-addr", "127.0.0.1", "--master-port", str(port),
+                          _os.path.join(here, "multigpu_worker.py")], capture_output=True, text=True, timeout=900)
+    assert res.returncode == 0, res.stdout[-3000:] + res.stderr[-3000:]
+    assert res.stdout.count("MULTIGPU_OK") == nranks, res.stdout[-2000:]

@@ -63,6 +63,7 @@ EXPORTS = [
     "trixib200_alloc", "trixib200_free", "trixib200_upload", "trixib200_download", "trixib200_sync",
     "trixib200_stream", "trixib200_fill_initial_condition", "trixib200_rk2n_update", "trixib200_time_rhs",
     "trixib200_launch_count", "trixib200_comm_unique_id", "trixib200_comm_init", "trixib200_set_stream",
+    "trixib200_rhs_host", "trixib200_host_register", "trixib200_host_unregister",
     "trixib200_plan_create", "trixib200_plan_destroy", "trixib200_plan_len", "trixib200_plan_get",
 ]
 
@@ -110,6 +111,9 @@ def lib():
     L.trixib200_size.restype = C.c_int64
     L.trixib200_size.argtypes = [C.c_void_p, C.c_char_p]
     L.trixib200_rhs.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_double]
+    L.trixib200_rhs_host.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_double]
+    L.trixib200_host_register.argtypes = [C.c_void_p, C.c_void_p, C.c_int64]
+    L.trixib200_host_unregister.argtypes = [C.c_void_p, C.c_void_p]
     L.trixib200_max_dt.argtypes = [C.c_void_p, C.c_void_p, C.c_double, C.POINTER(C.c_double)]
     L.trixib200_stage.argtypes = [C.c_void_p, C.c_char_p, C.c_void_p, C.c_void_p, C.c_double]
     L.trixib200_cache_len.restype = C.c_int64

@@ -243,6 +243,8 @@ struct trixib200_handle {
   std::vector<int64_t> peer_count;        // faces exchanged with each peer (send == recv count)
   ncclComm_t comm = nullptr;
   int sm_count = 148;
+  // rhs_host: library-owned device mirrors of the caller's host vectors
+  double* host_u = nullptr; double* host_du = nullptr;
 };
 
 template <class T> static int upload(trixib200_handle* h, const std::vector<T>& v, T** out) {
@@ -696,6 +698,35 @@ extern "C" int trixib200_rhs(trixib200_handle* h, double* du, const double* u, d
   int rc = h->fused ? rhs_fused(h, du, u, t) : rhs_staged(h, du, u, t);
   if (rc) return rc;
   CUDA_TRY(cudaGetLastError());
+  return 0;
+}
+
+// ---------------------------------------------------------------------------------------------- rhs on host vectors
+extern "C" int trixib200_rhs_host(trixib200_handle* h, double* du_host, const double* u_host, double t) {
+  if (!h || !du_host || !u_host) return fail(TRIXIB200_EINVAL, "null argument");
+  CUDA_TRY(cudaSetDevice(h->cfg.device));
+  const Dev& d = h->d;
+  const size_t n = (size_t)d.E * d.nn * d.nv;
+  if (!h->host_u) {
+    if (int rc = dalloc(h, n, &h->host_u, false)) return rc;
+    if (int rc = dalloc(h, n, &h->host_du, false)) return rc;
+  }
+  CUDA_TRY(cudaMemcpyAsync(h->host_u, u_host, n * sizeof(double), cudaMemcpyHostToDevice, h->stream));
+  if (int rc = trixib200_rhs(h, h->host_du, h->host_u, t)) return rc;
+  CUDA_TRY(cudaMemcpyAsync(du_host, h->host_du, n * sizeof(double), cudaMemcpyDeviceToHost, h->stream));
+  CUDA_TRY(cudaStreamSynchronize(h->stream));
+  return 0;
+}
+extern "C" int trixib200_host_register(trixib200_handle* h, double* host, int64_t n) {
+  if (!h || !host || n < 0) return fail(TRIXIB200_EINVAL, "bad argument");
+  CUDA_TRY(cudaSetDevice(h->cfg.device));
+  CUDA_TRY(cudaHostRegister(host, (size_t)n * sizeof(double), cudaHostRegisterDefault));
+  return 0;
+}
+extern "C" int trixib200_host_unregister(trixib200_handle* h, double* host) {
+  if (!h || !host) return fail(TRIXIB200_EINVAL, "bad argument");
+  CUDA_TRY(cudaSetDevice(h->cfg.device));
+  CUDA_TRY(cudaHostUnregister(host));
   return 0;
 }
 

@@ -216,6 +216,14 @@ class SemidiscretizationHyperbolicGPU:
         self._sync_stream()
         _lib.check(self._L.trixib200_rhs(self._h, du.data_ptr(), u.data_ptr(), float(t)))
 
+    def rhs_host(self, du_host, u_host, t):
+        """`rhs!(du_ode, u_ode, semi, t)` on HOST vectors (numpy float64 or CPU torch tensors, ideally pinned):
+        upload, rhs!, download inside the library (trixib200_rhs_host)."""
+        self._sync_stream()
+        pu = u_host.data_ptr() if hasattr(u_host, "data_ptr") else u_host.ctypes.data
+        pdu = du_host.data_ptr() if hasattr(du_host, "data_ptr") else du_host.ctypes.data
+        _lib.check(self._L.trixib200_rhs_host(self._h, pdu, pu, float(t)))
+
     def max_dt(self, u, t=0.0):
         self._sync_stream()
         out = C.c_double()
