@@ -46,7 +46,8 @@ enum { TRIXIB200_SRC_NONE = 0, TRIXIB200_SRC_CONVERGENCE_TEST = 1 };
 
 /* flags */
 enum { TRIXIB200_FLAG_STAGED_ONLY = 1,     /* force the staged (materialising) kernels; debugging / stage parity */
-       TRIXIB200_FLAG_NO_WARP_KERNEL = 2 }; /* keep the thread-per-node fused kernel where the warp-per-element one applies */
+       TRIXIB200_FLAG_NO_WARP_KERNEL = 2,  /* keep the thread-per-node fused kernel where the warp-per-element one applies */
+       TRIXIB200_FLAG_NO_LINE_KERNEL = 4 }; /* keep the warp-per-element kernel where the line-owner one applies */
 
 typedef struct trixib200_config {
   int32_t ndim;                 /* 1, 2, 3 */
@@ -120,7 +121,8 @@ int trixib200_destroy(trixib200_handle* h);
 /* sizes: "nelements" (local), "nelements_global", "first_element" (0-based global index of the first local
  * element), "nvars", "nnodes", "ndofs" (local, per field), "nunknowns" (local length of u), "ninterfaces",
  * "nboundaries", "nmortars", "nhalo_faces", "fused" (1 if a fused kernel is active), "warp3d" (1 if the
- * warp-per-element 3D flux-differencing kernel is the one in use) */
+ * warp-per-element 3D flux-differencing kernel is available), "line3d" (1 if the line-owner 3D Euler
+ * flux-differencing kernel is the one in use) */
 int64_t trixib200_size(const trixib200_handle* h, const char* name);
 
 /* replaces: rhs_gpu!(du_ode, u_ode, semi, t) (reference src/solvers/solvers.jl:18-31 -> src/solvers/dg_3d.jl:895-925).

@@ -76,7 +76,7 @@ def test_stages_match_oracle(name):
         assert np.abs(semi.cache("alpha") - o.f64("alpha")).max() <= 1e-12
 
 
-@pytest.mark.parametrize("kernel", ["staged", "fused", "fused_node"])
+@pytest.mark.parametrize("kernel", ["staged", "fused", "fused_node", "fused_warp"])
 @pytest.mark.parametrize("name", sorted(CASES))
 def test_rhs_matches_oracle(name, kernel):
     """Whole rhs!: du within 1e-12 (relative max-norm) of the CPU reference after one call, for every kernel
@@ -84,11 +84,14 @@ def test_rhs_matches_oracle(name, kernel):
     (thread-per-node fused kernel forced)."""
     c = CASES[name]
     o = make_oracle(c)
-    semi = make_semi(c, staged_only=(kernel == "staged"), no_warp_kernel=(kernel == "fused_node"))
+    semi = make_semi(c, staged_only=(kernel == "staged"), no_warp_kernel=(kernel == "fused_node"),
+                     no_line_kernel=(kernel == "fused_warp"))
     if kernel != "staged" and not semi.fused:
         pytest.skip("fused kernels cover polydeg 3 in 2D/3D; this case runs the staged kernels")
     if kernel == "fused_node" and not make_semi(c).warp3d:
         pytest.skip("the default fused kernel already is the thread-per-node one here")
+    if kernel == "fused_warp" and not make_semi(c).line3d:
+        pytest.skip("the default fused kernel already is the warp-per-element (or node) one here")
     for t0 in (0.0, 0.37):
         u = o.compute_coefficients(t0)
         du_ref = o.rhs(u, t0)
@@ -107,7 +110,8 @@ def test_fused_equals_staged_on_random_state(name):
     c = CASES[name]
     o, fused, staged = make_oracle(c), make_semi(c), make_semi(c, staged_only=True)
     fused_node = make_semi(c, no_warp_kernel=True)
-    assert fused.fused and not staged.fused and not fused_node.warp3d
+    fused_warp = make_semi(c, no_line_kernel=True)
+    assert fused.fused and not staged.fused and not fused_node.warp3d and not fused_warp.line3d
     rng = np.random.default_rng(7)
     u = o.compute_coefficients(0.0)
     nv = o.nvars
@@ -119,12 +123,13 @@ def test_fused_equals_staged_on_random_state(name):
     u = uu.ravel()
     du_ref = o.rhs(u, 0.0)
     outs = []
-    for semi in (fused, staged, fused_node):
+    for semi in (fused, staged, fused_node, fused_warp):
         u_d, du_d = _to_dev(semi, u), semi.new_vector()
         semi.rhs(du_d, u_d, 0.0)
         outs.append(du_d.cpu().numpy())
         assert rel_max_err(outs[-1], du_ref) <= TOL
     assert rel_max_err(outs[0], outs[1]) <= TOL and rel_max_err(outs[2], outs[1]) <= TOL
+    assert rel_max_err(outs[3], outs[1]) <= TOL
 
 
 @pytest.mark.parametrize("name", sorted(CASES))

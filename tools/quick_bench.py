@@ -13,7 +13,8 @@ for staged in (False,):
             continue
         c = dict(cases.CASES["c5_euler_ec_3d"], level=lv)
         t0 = time.time()
-        semi = cases.make_semi(c, staged_only=(kern == "staged"), no_warp_kernel=(kern == "node"), node_coordinates=False)
+        semi = cases.make_semi(c, staged_only=(kern == "staged"), no_warp_kernel=(kern == "node"),
+                               no_line_kernel=(kern == "warp"), node_coordinates=False)
         t1 = time.time()
         u = semi.compute_coefficients_gpu(0.0, on_device=True)
         du = semi.new_vector()
@@ -23,7 +24,7 @@ for staged in (False,):
         reps = 20
         ms = semi.time_rhs(du, u, 0.0, reps) / reps
         nd = semi.ndofs()
-        print(f"level {lv} kern={kern} warp3d={semi.warp3d} E={semi.nelements} setup {t1-t0:.1f}s rhs {ms:.4f} ms  "
+        print(f"level {lv} kern={kern} line3d={semi.line3d} E={semi.nelements} setup {t1-t0:.1f}s rhs {ms:.4f} ms  "
               f"{nd/ms/1e6:.2f} GDOF/s  algo-HBM {81*nd/ms/1e6:.0f} GB/s", flush=True)
         del semi, u, du
         torch.cuda.empty_cache()

@@ -16,6 +16,7 @@
 #include "kernels_staged.cuh"
 #include "kernels_fused.cuh"
 #include "kernels_warp3d.cuh"
+#include "kernels_line3d.cuh"
 
 using namespace tb;
 
@@ -234,7 +235,8 @@ struct trixib200_handle {
   std::vector<void*> allocs;
   double* d_scalar = nullptr;
   int64_t launches = 0;
-  bool fused = false, warp3d = false;
+  bool fused = false, warp3d = false, line3d = false;
+  LineOps line_ops;
   // fused-path element lists (multi-GPU overlap): interior first, then elements touching a halo face
   int* d_elems_interior = nullptr; int* d_elems_halo = nullptr;
   int64_t n_interior = 0, n_halo_elems = 0;
@@ -489,6 +491,9 @@ static int create_impl(const trixib200_config* cfg, const trixib200_basis_host* 
   // ---- fused path availability (3D/2D, polydeg 3) and its element lists
   h->fused = !(c.flags & TRIXIB200_FLAG_STAGED_ONLY) && fused_available(c);
   h->warp3d = h->fused && !(c.flags & TRIXIB200_FLAG_NO_WARP_KERNEL) && warp3d_available(c);
+  h->line3d = h->warp3d && !(c.flags & TRIXIB200_FLAG_NO_LINE_KERNEL) && line3d_available(c);
+  for (int i = 0; i < 16; ++i) h->line_ops.ds[i] = ops.Dsplit[(i & 3) + N * (i >> 2)];
+  h->line_ops.factor_1 = ops.factor_1; h->line_ops.factor_2 = ops.factor_2;
   {
     int* p;
     if (int rc = upload(h, P.face_nbr, &p)) return rc;
@@ -543,6 +548,7 @@ extern "C" int64_t trixib200_size(const trixib200_handle* h, const char* name) {
   if (n == "nhalo_faces") return d.nhalo_recv;
   if (n == "fused") return h->fused ? 1 : 0;
   if (n == "warp3d") return h->warp3d ? 1 : 0;
+  if (n == "line3d") return h->line3d ? 1 : 0;
   if (n == "npeers") return (int64_t)h->peers.size();
   return -1;
 }
@@ -674,9 +680,11 @@ static int rhs_fused(trixib200_handle* h, double* du, const double* u, double t)
   bool multi = h->cfg.nranks > 1 && d.nhalo_send > 0;
   // warp-per-element kernel (3D flux differencing, polydeg 3) when its 16-byte copies are aligned
   const bool w3 = h->warp3d && ((((uintptr_t)u) | ((uintptr_t)du)) & 15) == 0;
+  const bool l3 = w3 && h->line3d;
   auto launch = [&](const int* elems, int64_t count) -> int {
     if (count <= 0) return 0;
-    int rc = w3 ? warp3d_launch(h->cfg, d, du, u, t, elems, count, h->stream, h->sm_count)
+    int rc = l3 ? line3d_launch(h->cfg, d, h->line_ops, du, u, t, elems, count, h->stream, h->sm_count)
+           : w3 ? warp3d_launch(h->cfg, d, du, u, t, elems, count, h->stream, h->sm_count)
                 : fused_launch(h->cfg, d, du, u, t, elems, count, h->stream, h->sm_count);
     if (rc) return fail(rc, "fused launch failed");
     h->launches++;

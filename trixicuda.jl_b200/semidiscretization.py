@@ -27,7 +27,8 @@ def _torch():
 
 class SemidiscretizationHyperbolicGPU:
     def __init__(self, mesh: TreeMesh, equations, initial_condition, solver, source_terms=None,
-                 boundary_conditions=boundary_condition_periodic, staged_only=False, no_warp_kernel=False, device=None,
+                 boundary_conditions=boundary_condition_periodic, staged_only=False, no_warp_kernel=False, no_line_kernel=False,
+                 device=None,
                  rank=0, nranks=1, comm_id=None, node_coordinates="auto"):
         if mesh.ndim != equations.ndim:
             raise ValueError("mesh and equations have different dimensions")
@@ -40,7 +41,7 @@ class SemidiscretizationHyperbolicGPU:
         self.device_index = torch.cuda.current_device() if device is None else int(device)
         self.device = torch.device("cuda", self.device_index)
         self.cache_cpu = init_containers(mesh, solver.basis.nodes)   # what Trixi's init_* give the Julia shim
-        self._create(staged_only, comm_id, node_coordinates, no_warp_kernel)
+        self._create(staged_only, comm_id, node_coordinates, no_warp_kernel, no_line_kernel)
 
     # ------------------------------------------------------------------ handle construction
     def _config(self, staged_only):
@@ -130,11 +131,13 @@ class SemidiscretizationHyperbolicGPU:
         mh.mortars_orientations = i64(c.mortars.orientations)
         return bh, mh, keep
 
-    def _create(self, staged_only, comm_id, node_coordinates, no_warp_kernel=False):
+    def _create(self, staged_only, comm_id, node_coordinates, no_warp_kernel=False, no_line_kernel=False):
         L = _lib.lib()
         cfg = self._config(staged_only)
         if no_warp_kernel:
             cfg.flags |= _lib.FLAG_NO_WARP_KERNEL
+        if no_line_kernel:
+            cfg.flags |= _lib.FLAG_NO_LINE_KERNEL
         bh, mh, keep = self._host_structs(node_coordinates)
         h = C.c_void_p()
         _lib.check(L.trixib200_create(C.byref(cfg), C.byref(bh), C.byref(mh), C.byref(h)))
@@ -149,6 +152,7 @@ class SemidiscretizationHyperbolicGPU:
         self.nelements_global = self.size("nelements_global")
         self.fused = bool(self.size("fused"))
         self.warp3d = bool(self.size("warp3d"))
+        self.line3d = bool(self.size("line3d"))
         self._stream = None
 
     def __del__(self):
