@@ -33,3 +33,11 @@ for a, s, st in ins:
 print("executed-weighted avg stall after FP64: %.2f" % (tot_s / tot_e))
 print("FP64 exec by stall count:", {k: round(100 * v / tot_e, 1) for k, v in sorted(hist.items())})
 print("sum of encoded stalls per executed instruction (min issue cycles/inst): %.2f" % (allst / alle))
+byop = collections.Counter(); byop_n = collections.Counter()
+for a, s, st in ins:
+    e, sm = ex.get(a, (0, 0))
+    op = re.sub(r'^@!?U?P\d+\s+', '', s).split()[0].split('.')[0]
+    byop[op] += e * max(st, 1); byop_n[op] += e
+print("encoded issue cycles by opcode (share of total, avg stall):")
+for op, v in byop.most_common(16):
+    print("  %-8s %5.1f%%  avg %.2f  n/iter %.0f" % (op, 100 * v / allst, v / byop_n[op], byop_n[op] / (alle / (allst and 1)) if False else byop_n[op]))

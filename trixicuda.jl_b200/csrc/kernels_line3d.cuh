@@ -192,12 +192,13 @@ __device__ __noinline__ L3Vec5 l3_source(const Dev* dp, int64_t e, int n, int i,
 // at 200 registers and 12 at 168 (accumulator tile aliased onto the staging buffer to fit) spill and run 1.4-1.6x
 // slower -- this kernel wants registers (8 independent flux chains per lane), not occupancy.
 //
-// Phase `dir` reads the velocity / momentum rows of the shared tiles rotated so that slot 0 is the component normal
-// to the lines, which makes every flux an orientation-1 flux. The hot path is branch-free (given fluxes of boundary
-// / mortar faces override the computed ones by selects; the last iteration prefetches its own element again): with
-// branches ptxas duplicated the flux code per path (245 KB of SASS, 15 % "no instruction" stalls, see
-// profiles/r1_ncu_line3d_v2_l6.json), and running the three phases through one copy of the code with a run-time
-// `dir` added ~180 integer instructions per DOF (profiles/r1_ncu_line3d_v3_l6.json).
+// The three phases run through ONE copy of the flux code (`dir` is a run-time value): phase `dir` reads the velocity
+// / momentum rows of the shared tiles rotated so that slot 0 is the component normal to the lines, which makes every
+// flux an orientation-1 flux, and only ~20 address computations per phase depend on `dir`. Unrolled phases give a
+// 40-60 KB loop body, beyond the 32 KB L1.5 instruction cache: 15-16 % "no instruction" stalls
+// (profiles/r1_ncu_line3d_v2_l6.json, r1_ncu_line3d_v4_l6.json). The hot path is also branch-free where ptxas would
+// otherwise duplicate the flux code per path (given fluxes of boundary / mortar faces override the computed ones by
+// selects; the last iteration prefetches its own element again).
 template <int VFLUX, int SFLUX, int WARPS>
 __global__ void __launch_bounds__(32 * WARPS, 2)
 k_line3d(const __grid_constant__ Dev d, const __grid_constant__ LineOps ops, double* __restrict__ du,
@@ -279,6 +280,14 @@ k_line3d(const __grid_constant__ Dev d, const __grid_constant__ LineOps ops, dou
   using D0 = std::integral_constant<int, 0>;
   using D1 = std::integral_constant<int, 1>;
   using D2 = std::integral_constant<int, 2>;
+  // swizzled tile positions of this lane's four line nodes per direction, one byte each
+  unsigned pk0 = 0, pk1 = 0, pk2 = 0;
+#pragma unroll
+  for (int m = 0; m < 4; ++m) {
+    pk0 |= (unsigned)l3_swz(m, la, lb) << (8 * m);
+    pk1 |= (unsigned)l3_swz(la, m, lb) << (8 * m);
+    pk2 |= (unsigned)l3_swz(la, lb, m) << (8 * m);
+  }
   int code[6] = {NB_SFV, NB_SFV, NB_SFV, NB_SFV, NB_SFV, NB_SFV};
   int64_t pr = wid;
   bool valid = false;
@@ -326,16 +335,15 @@ k_line3d(const __grid_constant__ Dev d, const __grid_constant__ LineOps ops, dou
     cp_async_commit();
 
     double acc[4][NV];
-    auto phase = [&](auto dir_tag) {
-      constexpr int dir = decltype(dir_tag)::value;
+#pragma unroll 1
+    for (int dir = 0; dir < 3; ++dir) {
       // rows of the velocity / momentum components in slot order (slot 0 = normal component)
-      constexpr int r0 = (1 + dir) * NN, r1 = (1 + (dir + 1) % 3) * NN, r2 = (1 + (dir + 2) % 3) * NN;
-      constexpr int c0 = 1 + dir, c1 = 1 + (dir + 1) % 3, c2 = 1 + (dir + 2) % 3;
-      const int c_lo = code[2 * dir], c_hi = code[2 * dir + 1];
-      int pos[4];
-#pragma unroll
-      for (int m = 0; m < 4; ++m)
-        pos[m] = dir == 0 ? l3_swz(m, la, lb) : (dir == 1 ? l3_swz(la, m, lb) : l3_swz(la, lb, m));
+      const int c0 = 1 + dir, c1 = (dir == 2) ? 1 : dir + 2, c2 = (dir == 0) ? 3 : dir;
+      const int r0 = c0 * NN, r1 = c1 * NN, r2 = c2 * NN;
+      const int c_lo = dir == 0 ? code[0] : (dir == 1 ? code[2] : code[4]);
+      const int c_hi = dir == 0 ? code[1] : (dir == 1 ? code[3] : code[5]);
+      const unsigned pk = dir == 0 ? pk0 : (dir == 1 ? pk1 : pk2);
+      const int pos[4] = {(int)(pk & 0xff), (int)((pk >> 8) & 0xff), (int)((pk >> 16) & 0xff), (int)(pk >> 24)};
       // ---- this direction's traces have landed (three younger groups may still be in flight)
       cp_async_wait<3>();
       __syncwarp();
@@ -461,12 +469,11 @@ k_line3d(const __grid_constant__ Dev d, const __grid_constant__ LineOps ops, dou
         }
       }
       __syncwarp();   // traces consumed, accumulators visible; after the z phase: every lane is done with sq
-      issue_traces(dir_tag, e_next, code_next[2 * dir], code_next[2 * dir + 1]);
+      if (dir == 0) issue_traces(D0{}, e_next, code_next[0], code_next[1]);
+      else if (dir == 1) issue_traces(D1{}, e_next, code_next[2], code_next[3]);
+      else issue_traces(D2{}, e_next, code_next[4], code_next[5]);
       cp_async_commit();
-    };
-    phase(D0{});
-    phase(D1{});
-    phase(D2{});
+    }
     // ---- Jacobian, sources, output. After the z phase the slots hold the components (z, x, y).
 #pragma unroll
     for (int m = 0; m < 4; ++m) {
