@@ -270,6 +270,28 @@ def test_rhs_host_matches_device_path(name):
     assert np.array_equal(du_d.cpu().numpy(), du_np)
 
 
+@pytest.mark.parametrize("name,level", [("c5_euler_ec_3d", 3), ("c2_euler_ec_2d", 5), ("advection_basic_3d", 3)])
+def test_rhs_host_chunk_pipeline(name, level, monkeypatch):
+    """The chunked upload / compute / download pipeline of trixib200_rhs_host (forced to 64-element chunks so that
+    a small mesh has many chunks with neighbours in other chunks) gives bitwise the resident-vector result."""
+    torch = _torch()
+    monkeypatch.setenv("TRIXIB200_HOST_CHUNK", "64")
+    c = dict(CASES[name], level=level)
+    o, semi = make_oracle(c), make_semi(c, level=level)
+    u = o.compute_coefficients(0.0)
+    du_ref = o.rhs(u, 0.0)
+    u_h = torch.from_numpy(u).pin_memory()
+    du_h = torch.full_like(u_h, float("nan")).pin_memory()
+    for _ in range(3):
+        du_h.fill_(float("nan"))
+        semi.rhs_host(du_h, u_h, 0.0)
+        assert rel_max_err(du_h.numpy(), du_ref) <= TOL
+    u_d, du_d = _to_dev(semi, u), semi.new_vector()
+    semi.rhs(du_d, u_d, 0.0)
+    assert np.array_equal(du_d.cpu().numpy(), du_h.numpy())
+    assert semi.launch_count() > 3 * 8          # one launch per chunk
+
+
 @pytest.mark.parametrize("nranks", [2, 4, 8])
 def test_multi_gpu_rhs_matches_oracle(nranks):
     """Morton-curve partition over `nranks` GPUs of this box (one process per GPU, NCCL halo exchange)."""

@@ -8,6 +8,7 @@
 #include <cmath>
 #include <cstdio>
 #include <cstring>
+#include <cstdlib>
 #include <cstdint>
 #include <string>
 #include <vector>
@@ -245,8 +246,19 @@ struct trixib200_handle {
   std::vector<int64_t> peer_count;        // faces exchanged with each peer (send == recv count)
   ncclComm_t comm = nullptr;
   int sm_count = 148;
-  // rhs_host: library-owned device mirrors of the caller's host vectors
+  // rhs_host: library-owned device mirrors of the caller's host vectors, and the chunk pipeline
   double* host_u = nullptr; double* host_du = nullptr;
+  std::vector<int> face_nbr_host;          // kept for the chunk dependency analysis
+  std::vector<double> chunk_key_src;       // last-dimension coordinate of every element (upload ordering)
+  struct HostPipe {
+    bool built = false, usable = false;
+    int64_t ce = 0, nchunks = 0;
+    std::vector<int> upload_order;         // chunk ids in upload order
+    std::vector<std::vector<int>> ready;   // ready[i]: chunks computable once upload_order[i] has landed
+    std::vector<cudaEvent_t> ev_in, ev_done;
+    cudaStream_t s_in = nullptr, s_out = nullptr;
+    int* d_iota = nullptr;
+  } pipe;
 };
 
 template <class T> static int upload(trixib200_handle* h, const std::vector<T>& v, T** out) {
@@ -321,6 +333,10 @@ extern "C" int trixib200_destroy(trixib200_handle* h) {
   if (h->ev_halo) cudaEventDestroy(h->ev_halo);
   if (h->ev_a) cudaEventDestroy(h->ev_a);
   if (h->ev_b) cudaEventDestroy(h->ev_b);
+  for (cudaEvent_t e : h->pipe.ev_in) cudaEventDestroy(e);
+  for (cudaEvent_t e : h->pipe.ev_done) cudaEventDestroy(e);
+  if (h->pipe.s_in) cudaStreamDestroy(h->pipe.s_in);
+  if (h->pipe.s_out) cudaStreamDestroy(h->pipe.s_out);
   if (h->comm_stream) cudaStreamDestroy(h->comm_stream);
   if (h->stream && h->owns_stream) cudaStreamDestroy(h->stream);
   delete h;
@@ -498,6 +514,12 @@ static int create_impl(const trixib200_config* cfg, const trixib200_basis_host* 
     int* p;
     if (int rc = upload(h, P.face_nbr, &p)) return rc;
     d.face_nbr = p;
+    h->face_nbr_host = P.face_nbr;
+    h->chunk_key_src.assign((size_t)E, 0.0);
+    for (int64_t e = 0; e < E; ++e) {
+      if (ms->cell_centers) h->chunk_key_src[e] = ms->cell_centers[(size_t)nd * (first + e) + (nd - 1)];
+      else if (ms->node_coordinates) h->chunk_key_src[e] = ms->node_coordinates[(size_t)nd * d.nn * (first + e) + (nd - 1)];
+    }
     h->n_interior = (int64_t)P.elems_interior.size(); h->n_halo_elems = (int64_t)P.elems_halo.size();
     if (int rc = upload(h, P.elems_interior, &p)) return rc; h->d_elems_interior = p;
     if (int rc = upload(h, P.elems_halo, &p)) return rc; h->d_elems_halo = p;
@@ -670,6 +692,20 @@ static int rhs_staged(trixib200_handle* h, double* du, const double* u, double t
   return 0;
 }
 
+// one launch of the best fused kernel over a list (or, with elems == nullptr, the first `count`) of elements
+static int fused_launch_any(trixib200_handle* h, double* du, const double* u, double t, const int* elems, int64_t count) {
+  if (count <= 0) return 0;
+  Dev& d = h->d;
+  const bool w3 = h->warp3d && ((((uintptr_t)u) | ((uintptr_t)du)) & 15) == 0;
+  const bool l3 = w3 && h->line3d;
+  int rc = l3 ? line3d_launch(h->cfg, d, h->line_ops, du, u, t, elems, count, h->stream, h->sm_count)
+         : w3 ? warp3d_launch(h->cfg, d, du, u, t, elems, count, h->stream, h->sm_count)
+              : fused_launch(h->cfg, d, du, u, t, elems, count, h->stream, h->sm_count);
+  if (rc) return fail(rc, "fused launch failed");
+  h->launches++;
+  return 0;
+}
+
 static int rhs_fused(trixib200_handle* h, double* du, const double* u, double t) {
   Dev& d = h->d;
   if (int rc = halo_begin(h, u)) return rc;
@@ -678,18 +714,8 @@ static int rhs_fused(trixib200_handle* h, double* du, const double* u, double t)
   if (d.B > 0) { st_prolong_boundaries(h, u); st_boundary_flux(h, t); }
   if (d.M > 0) { st_prolong_mortars(h, u); st_mortar_flux(h); }
   bool multi = h->cfg.nranks > 1 && d.nhalo_send > 0;
-  // warp-per-element kernel (3D flux differencing, polydeg 3) when its 16-byte copies are aligned
-  const bool w3 = h->warp3d && ((((uintptr_t)u) | ((uintptr_t)du)) & 15) == 0;
-  const bool l3 = w3 && h->line3d;
-  auto launch = [&](const int* elems, int64_t count) -> int {
-    if (count <= 0) return 0;
-    int rc = l3 ? line3d_launch(h->cfg, d, h->line_ops, du, u, t, elems, count, h->stream, h->sm_count)
-           : w3 ? warp3d_launch(h->cfg, d, du, u, t, elems, count, h->stream, h->sm_count)
-                : fused_launch(h->cfg, d, du, u, t, elems, count, h->stream, h->sm_count);
-    if (rc) return fail(rc, "fused launch failed");
-    h->launches++;
-    return 0;
-  };
+  // (the line-owner / warp-per-element kernels need 16-byte aligned vectors; fused_launch_any checks)
+  auto launch = [&](const int* elems, int64_t count) -> int { return fused_launch_any(h, du, u, t, elems, count); };
   if (!multi) {
     if (int rc = launch(nullptr, d.E)) return rc;
   } else {
@@ -710,6 +736,59 @@ extern "C" int trixib200_rhs(trixib200_handle* h, double* du, const double* u, d
 }
 
 // ---------------------------------------------------------------------------------------------- rhs on host vectors
+// Chunk pipeline of trixib200_rhs_host. The local elements are cut into contiguous chunks of the Morton order; chunks
+// are uploaded in the order of their last-dimension coordinate (thin layers), a chunk's elements are computed as soon
+// as the chunks holding all their face neighbours have landed, and its du is downloaded right after: upload, kernels
+// and download overlap (PCIe is full duplex) instead of running back to back. Used when one fused launch is the whole
+// rhs! (single rank, no boundary / mortar faces, no shock-capturing indicator pass); otherwise the plain sequence.
+static int build_host_pipe(trixib200_handle* h) {
+  auto& P = h->pipe;
+  P.built = true;
+  const Dev& d = h->d;
+  P.usable = h->fused && h->cfg.nranks == 1 && d.B == 0 && d.M == 0 &&
+             d.volume_integral != TRIXIB200_VI_SHOCK_CAPTURING_HG && !h->face_nbr_host.empty();
+  const int64_t E = d.E;
+  int64_t ce = 4096;   // elements per chunk (10 MB of 3D Euler state); TRIXIB200_HOST_CHUNK overrides (tests, tuning)
+  const char* env = getenv("TRIXIB200_HOST_CHUNK");
+  if (env && atoll(env) >= 64) ce = atoll(env);
+  P.usable = P.usable && E >= 4 * ce;
+  if (!P.usable) return 0;
+  P.ce = ce;
+  P.nchunks = (E + ce - 1) / ce;
+  const int nf = 2 * d.ndim;
+  // upload order: by the last-dimension coordinate of the chunk's first element, ties in Morton order
+  std::vector<int> order(P.nchunks);
+  for (int64_t c = 0; c < P.nchunks; ++c) order[c] = (int)c;
+  std::stable_sort(order.begin(), order.end(), [&](int a, int b) {
+    return h->chunk_key_src[(size_t)a * ce] < h->chunk_key_src[(size_t)b * ce];
+  });
+  std::vector<int> upos(P.nchunks);
+  for (int64_t i = 0; i < P.nchunks; ++i) upos[order[i]] = (int)i;
+  P.upload_order = order;
+  P.ready.assign(P.nchunks, {});
+  for (int64_t c = 0; c < P.nchunks; ++c) {
+    int r = upos[c];
+    const int64_t e0 = c * ce, e1 = std::min(E, e0 + ce);
+    for (int64_t e = e0; e < e1; ++e)
+      for (int f = 0; f < nf; ++f) {
+        const int code = h->face_nbr_host[(size_t)e * nf + f];
+        if (code >= 0) r = std::max(r, upos[code / ce]);
+      }
+    P.ready[r].push_back((int)c);
+  }
+  CUDA_TRY(cudaStreamCreateWithFlags(&P.s_in, cudaStreamNonBlocking));
+  CUDA_TRY(cudaStreamCreateWithFlags(&P.s_out, cudaStreamNonBlocking));
+  P.ev_in.resize(P.nchunks); P.ev_done.resize(P.nchunks);
+  for (int64_t c = 0; c < P.nchunks; ++c) {
+    CUDA_TRY(cudaEventCreateWithFlags(&P.ev_in[c], cudaEventDisableTiming));
+    CUDA_TRY(cudaEventCreateWithFlags(&P.ev_done[c], cudaEventDisableTiming));
+  }
+  std::vector<int> iota((size_t)E);
+  for (int64_t e = 0; e < E; ++e) iota[e] = (int)e;
+  if (int rc = upload(h, iota, &P.d_iota)) return rc;
+  return 0;
+}
+
 extern "C" int trixib200_rhs_host(trixib200_handle* h, double* du_host, const double* u_host, double t) {
   if (!h || !du_host || !u_host) return fail(TRIXIB200_EINVAL, "null argument");
   CUDA_TRY(cudaSetDevice(h->cfg.device));
@@ -719,10 +798,53 @@ extern "C" int trixib200_rhs_host(trixib200_handle* h, double* du_host, const do
     if (int rc = dalloc(h, n, &h->host_u, false)) return rc;
     if (int rc = dalloc(h, n, &h->host_du, false)) return rc;
   }
-  CUDA_TRY(cudaMemcpyAsync(h->host_u, u_host, n * sizeof(double), cudaMemcpyHostToDevice, h->stream));
-  if (int rc = trixib200_rhs(h, h->host_du, h->host_u, t)) return rc;
-  CUDA_TRY(cudaMemcpyAsync(du_host, h->host_du, n * sizeof(double), cudaMemcpyDeviceToHost, h->stream));
+  if (!h->pipe.built)
+    if (int rc = build_host_pipe(h)) return rc;
+  auto& P = h->pipe;
+  if (!P.usable) {
+    CUDA_TRY(cudaMemcpyAsync(h->host_u, u_host, n * sizeof(double), cudaMemcpyHostToDevice, h->stream));
+    if (int rc = trixib200_rhs(h, h->host_du, h->host_u, t)) return rc;
+    CUDA_TRY(cudaMemcpyAsync(du_host, h->host_du, n * sizeof(double), cudaMemcpyDeviceToHost, h->stream));
+    CUDA_TRY(cudaStreamSynchronize(h->stream));
+    return 0;
+  }
+  // the previous work on the handle's stream may still read host_u / write host_du
+  CUDA_TRY(cudaEventRecord(h->ev_pack, h->stream));
+  CUDA_TRY(cudaStreamWaitEvent(P.s_in, h->ev_pack, 0));
+  const size_t per = (size_t)d.nn * d.nv;
+  // Optional (TRIXIB200_HOST_DIRECT=1) for page-locked du: the kernels store du straight into host memory (posted
+  // PCIe writes, 16-byte coalesced) instead of a copy stage. Measured on B200 / PCIe Gen5 at level 7: 144 ms per
+  // rhs! against 140 ms with the DMA download -- both sit on the duplex PCIe limit (2 x 5.37 GB), so it is off.
+  double* du_direct = nullptr;
+  {
+    static const bool allow = getenv("TRIXIB200_HOST_DIRECT") && atoi(getenv("TRIXIB200_HOST_DIRECT")) == 1;
+    cudaPointerAttributes at;
+    if (allow && cudaPointerGetAttributes(&at, du_host) == cudaSuccess && at.type == cudaMemoryTypeHost &&
+        at.devicePointer && (((uintptr_t)at.devicePointer) & 15) == 0)
+      du_direct = (double*)at.devicePointer;
+    cudaGetLastError();
+  }
+  for (int64_t i = 0; i < P.nchunks; ++i) {
+    const int cu = P.upload_order[i];
+    const int64_t e0 = (int64_t)cu * P.ce, cnt = std::min<int64_t>(d.E - e0, P.ce);
+    CUDA_TRY(cudaMemcpyAsync(h->host_u + per * e0, u_host + per * e0, per * cnt * sizeof(double),
+                             cudaMemcpyHostToDevice, P.s_in));
+    CUDA_TRY(cudaEventRecord(P.ev_in[i], P.s_in));
+    if (P.ready[i].empty()) continue;
+    CUDA_TRY(cudaStreamWaitEvent(h->stream, P.ev_in[i], 0));
+    for (int c : P.ready[i]) {
+      const int64_t c0 = (int64_t)c * P.ce, ccnt = std::min<int64_t>(d.E - c0, P.ce);
+      if (int rc = fused_launch_any(h, du_direct ? du_direct : h->host_du, h->host_u, t, P.d_iota + c0, ccnt)) return rc;
+      if (du_direct) continue;
+      CUDA_TRY(cudaEventRecord(P.ev_done[c], h->stream));
+      CUDA_TRY(cudaStreamWaitEvent(P.s_out, P.ev_done[c], 0));
+      CUDA_TRY(cudaMemcpyAsync(du_host + per * c0, h->host_du + per * c0, per * ccnt * sizeof(double),
+                               cudaMemcpyDeviceToHost, P.s_out));
+    }
+  }
+  CUDA_TRY(cudaStreamSynchronize(P.s_out));
   CUDA_TRY(cudaStreamSynchronize(h->stream));
+  CUDA_TRY(cudaGetLastError());
   return 0;
 }
 extern "C" int trixib200_host_register(trixib200_handle* h, double* host, int64_t n) {
