@@ -68,6 +68,13 @@ CASES = {
     "mhd_shock_3d": case(3, "mhd", level=2, vi="shock_capturing_hg", volume_flux="flux_hindenlang_gassner",
                          volume_flux_fv="flux_lax_friedrichs", surface_flux="flux_lax_friedrichs", noncons=True,
                          ic="weak_blast_wave", cmin=-2.0, cmax=2.0),
+    # 3D Euler flux differencing with faces whose flux is given (mortars, Dirichlet boundaries): the line-owner
+    # kernel consumes surface_flux_values on those faces
+    "euler_ec_mortar_3d": case(3, "euler", level=2, vi="flux_differencing", volume_flux="flux_ranocha",
+                               surface_flux="flux_ranocha", ic="weak_blast_wave", patches=BOX3),
+    "euler_fd_nonperiodic_3d": case(3, "euler", level=2, vi="flux_differencing", volume_flux="flux_ranocha",
+                                    surface_flux="flux_lax_friedrichs", source="convergence_test", bc="dirichlet_ic",
+                                    periodic=False, cmin=0.0, cmax=2.0),
     # other polynomial degrees go through the staged kernels
     "euler_ec_3d_p2": case(3, "euler", level=2, polydeg=2, vi="flux_differencing", volume_flux="flux_ranocha",
                            surface_flux="flux_ranocha", ic="weak_blast_wave", cmin=-2.0, cmax=2.0),

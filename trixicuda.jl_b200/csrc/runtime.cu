@@ -18,6 +18,7 @@
 #include "kernels_fused.cuh"
 #include "kernels_warp3d.cuh"
 #include "kernels_line3d.cuh"
+#include "kernels_line6.cuh"
 
 using namespace tb;
 
@@ -698,7 +699,10 @@ static int fused_launch_any(trixib200_handle* h, double* du, const double* u, do
   Dev& d = h->d;
   const bool w3 = h->warp3d && ((((uintptr_t)u) | ((uintptr_t)du)) & 15) == 0;
   const bool l3 = w3 && h->line3d;
-  int rc = l3 ? line3d_launch(h->cfg, d, h->line_ops, du, u, t, elems, count, h->stream, h->sm_count)
+  // TRIXIB200_LINE_KERNEL=5 selects the previous generation of the line-owner kernel (A/B measurements)
+  static const bool gen5 = getenv("TRIXIB200_LINE_KERNEL") && atoi(getenv("TRIXIB200_LINE_KERNEL")) == 5;
+  int rc = (l3 && !gen5) ? line6_launch(h->cfg, d, h->line_ops, du, u, t, elems, count, h->stream, h->sm_count)
+         : l3 ? line3d_launch(h->cfg, d, h->line_ops, du, u, t, elems, count, h->stream, h->sm_count)
          : w3 ? warp3d_launch(h->cfg, d, du, u, t, elems, count, h->stream, h->sm_count)
               : fused_launch(h->cfg, d, du, u, t, elems, count, h->stream, h->sm_count);
   if (rc) return fail(rc, "fused launch failed");
