@@ -246,7 +246,7 @@ def run_ours(args):
 
     if rank != 0:
         return 0
-    # ---- roofline of the dominant kernel (at N=1 the rhs! IS one launch of k_warp3d)
+    # ---- roofline of the dominant kernel (at N=1 the rhs! IS one launch of k_line6)
     peaks, peak_src = {}, "fallback"
     try:
         peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
@@ -257,7 +257,7 @@ def run_ours(args):
     achieved = BYTES_PER_DOF * ndofs_local / (ms_step * 1e-3) / 1e9
     traffic = None
     try:
-        traffic = json.load(open(os.path.join(ROOT, "profiles", "traffic.json"))).get("k_line3d_bytes_per_dof")
+        traffic = json.load(open(os.path.join(ROOT, "profiles", "traffic.json"))).get("k_line6_bytes_per_dof")
         traffic = traffic * ndofs_local if traffic is not None else None
     except Exception:
         pass
@@ -268,7 +268,7 @@ def run_ours(args):
         pass
     roofline = {"bound": "hbm", "achieved": achieved, "peak": hbm_peak, "unit": "GB/s", "frac": achieved / hbm_peak,
                 "traffic": traffic, "peak_source": peak_src + " (MEASURED_PEAKS.json hbm_gbs)",
-                "kernel": ("k_line3d<flux_ranocha, flux_ranocha, 4>" if semi.line3d else
+                "kernel": ("k_line6<flux_ranocha, flux_ranocha, SFV=0, 4 warps, 2 CTAs/SM, 8 pairs staged>" if semi.line3d else
                            "k_warp3d<EqEuler<3>, flux_ranocha, flux_ranocha>" if semi.warp3d else "k_fused"),
                 "algorithmic_bytes_per_dof": BYTES_PER_DOF,
                 "fp64": {"algorithmic_flop_per_dof": FLOP_PER_DOF,

@@ -13,5 +13,5 @@ cat gpurun_out/bench.json; tail -3 gpurun_out/bench.err
 timeout 300 python bench.py --impl reference --steps 5 --warmup 1 > gpurun_out/bench_ref.json 2> gpurun_out/bench_ref.err
 cat gpurun_out/bench_ref.json
 timeout 300 ncu --metrics gpu__time_duration.sum --clock-control none -c 40 --csv --log-file gpurun_out/launches.csv python tools/prof_target.py 6 4 > gpurun_out/ncu_launch.log 2>&1
-timeout 600 ncu --set full --clock-control none --import-source on -k regex:k_line3d -s 2 -c 1 -f -o gpurun_out/prof_warp3d python tools/prof_target.py 6 4 > gpurun_out/ncu_full.log 2>&1
+timeout 600 ncu --set full --clock-control none --import-source on -k regex:k_line6 -s 2 -c 1 -f -o gpurun_out/prof_line6 python tools/prof_target.py 6 4 > gpurun_out/ncu_full.log 2>&1
 ls -la gpurun_out

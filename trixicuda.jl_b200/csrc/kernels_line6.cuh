@@ -22,6 +22,7 @@
 #pragma once
 #include "kernels_line3d.cuh"
 
+
 namespace tb {
 
 constexpr int L6_TILE = 320;                          // 5 x 64 doubles
@@ -37,18 +38,21 @@ __device__ __noinline__ L3Vec5 l6_pair_correction(L6Pair p, double inv_gm1) {
   return r;
 }
 
-// Four two-point fluxes (orientation 1 in the rotated frame) between the virtual line nodes (A_k, B_k) of Q, staged
-// across the pairs so that consecutive instructions are independent. Returns the "needs the logarithmic branch" mask.
-template <bool FAST, int A0, int B0, int A1, int B1, int A2, int B2, int A3, int B3>
-TB_D unsigned l6_flux4(const double (&Q)[6][5], int kind_a, int kind_b, int kind_c, int kind_d, const EqPrm& prm,
-                       double (&F)[4][5]) {
-  constexpr int PA[4] = {A0, A1, A2, A3}, PB[4] = {B0, B1, B2, B3};
+// The 8 pairs of a line in evaluation order, as indices into the virtual nodes Q[0..5] = (low neighbour, nodes 0..3,
+// high neighbour): all pairs of node 0 first (they complete node 0), then node 1's, then the rest.
+__device__ constexpr int L6_PA[8] = {0, 1, 1, 1, 2, 2, 3, 4};
+__device__ constexpr int L6_PB[8] = {1, 2, 3, 4, 3, 4, 4, 5};
+
+// NP two-point fluxes (orientation 1 in the rotated frame) of the pairs K0 .. K0 + NP - 1, staged across the pairs so
+// that consecutive instructions are independent. Returns the "needs the logarithmic branch" mask (bit k - K0).
+template <bool FAST, int K0, int NP>
+TB_D unsigned l6_fluxes(const double (&Q)[6][5], int vflux, int sflux, const EqPrm& prm, double (&F)[NP][5]) {
   unsigned rough = 0;
   if (FAST) {
-    double s[4], r[4], dd[4], tt[4], rt[4], xy[4], rm[4], im[4];
+    double s[NP], r[NP], dd[NP], tt[NP], rt[NP], xy[NP], rm[NP], im[NP];
 #pragma unroll
-    for (int k = 0; k < 4; ++k) {
-      const double* a = Q[PA[k]]; const double* b = Q[PB[k]];
+    for (int k = 0; k < NP; ++k) {
+      const double* a = Q[L6_PA[K0 + k]]; const double* b = Q[L6_PB[K0 + k]];
       s[k] = a[0] + b[0];
       dd[k] = a[0] - b[0];
       const double x = a[0] * b[4], y = b[0] * a[4];
@@ -58,40 +62,58 @@ TB_D unsigned l6_flux4(const double (&Q)[6][5], int kind_a, int kind_b, int kind
       asm("rcp.approx.ftz.f64 %0, %1;" : "=d"(rt[k]) : "d"(tt[k]));
     }
 #pragma unroll
-    for (int k = 0; k < 4; ++k) {
+    for (int k = 0; k < NP; ++k) {
       r[k] = fma(r[k], fma(-s[k], r[k], 1.0), r[k]);
       const double e1 = fma(-tt[k], rt[k], 1.0);
       rt[k] = fma(rt[k], fma(e1, e1, e1), rt[k]);
     }
 #pragma unroll
-    for (int k = 0; k < 4; ++k) {
+    for (int k = 0; k < NP; ++k) {
       const double uu = dd[k] * r[k], f2 = uu * uu;
       const double ut = xy[k] * rt[k], g2 = ut * ut;
       rm[k] = s[k] * fma(f2, fma(f2, fma(f2, -22.0 / 945, -2.0 / 45), -1.0 / 6), 0.5);
-      im[k] = ((Q[PA[k]][4] * Q[PB[k]][4]) * rt[k]) * fma(g2, fma(g2, fma(g2, 2.0 / 7, 2.0 / 5), 2.0 / 3), 2.0);
+      im[k] = ((Q[L6_PA[K0 + k]][4] * Q[L6_PB[K0 + k]][4]) * rt[k]) * fma(g2, fma(g2, fma(g2, 2.0 / 7, 2.0 / 5), 2.0 / 3), 2.0);
       if (l3_is_rough(f2) || l3_is_rough(g2)) rough |= 1u << k;
     }
 #pragma unroll
-    for (int k = 0; k < 4; ++k) l3_ranocha_from_means<1>(Q[PA[k]], Q[PB[k]], rm[k], im[k], prm.inv_gm1, F[k]);
+    for (int k = 0; k < NP; ++k)
+      l3_ranocha_from_means<1>(Q[L6_PA[K0 + k]], Q[L6_PB[K0 + k]], rm[k], im[k], prm.inv_gm1, F[k]);
   } else {
-    const int kind[4] = {kind_a, kind_b, kind_c, kind_d};
 #pragma unroll
-    for (int k = 0; k < 4; ++k) l3_flux<1, -1>(kind[k], Q[PA[k]], Q[PB[k]], prm, F[k]);
+    for (int k = 0; k < NP; ++k) {
+      const bool surf = (K0 + k == 0) || (K0 + k == 7);
+      l3_flux<1, -1>(surf ? sflux : vflux, Q[L6_PA[K0 + k]], Q[L6_PB[K0 + k]], prm, F[k]);
+    }
   }
   return rough;
 }
 
-template <int VFLUX, int SFLUX, bool SFV, int WARPS, int CTAS>
-__global__ void __launch_bounds__(32 * WARPS, CTAS)
+// registers per thread that let CTAS CTAs of WARPS warps share the 64 K registers of an SM (allocation unit: 8 per thread)
+constexpr int l6_maxnreg(int warps, int ctas) {
+  const int r = (65536 / (32 * warps * ctas)) / 8 * 8;
+  return r > 255 ? 255 : r;
+}
+
+template <int VFLUX, int SFLUX, bool SFV, int WARPS, int CTAS, int NP>
+__global__ void __launch_bounds__(32 * WARPS) __maxnreg__(l6_maxnreg(WARPS, CTAS))
 k_line6(const __grid_constant__ Dev d, const __grid_constant__ LineOps ops, double* __restrict__ du,
         const double* __restrict__ u, double t, const int* __restrict__ elems, int64_t count) {
   constexpr int NV = 5, NN = 64;
   constexpr bool FAST = (VFLUX == TRIXIB200_FLUX_RANOCHA && SFLUX == TRIXIB200_FLUX_RANOCHA);
   extern __shared__ __align__(16) double smem_l6[];
-  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-  const int half = lane >> 4, l16 = lane & 15;
+  // Per-lane constants live in two OPAQUE registers (a self-shuffle hides their origin): under register pressure ptxas
+  // otherwise re-derives them from S2R SR_TID.X + an integer chain in every phase (short-scoreboard stalls at the top
+  // of each phase in profiles/r1_ncu_line6_a.txt); from the packed word they cost one or two ALU ops.
+  unsigned lp = threadIdx.x & 31;          // l16 | half << 4
+  unsigned sb = (unsigned)__cvta_generic_to_shared(smem_l6) +
+                (unsigned)((2 * (threadIdx.x >> 5) + ((threadIdx.x >> 4) & 1)) * L6_EL * sizeof(double));
+  // (a self-shuffle: ptxas cannot see through it, an empty asm only stops the front end)
+  lp = __shfl_sync(0xffffffffu, lp, threadIdx.x & 31);
+  sb = __shfl_sync(0xffffffffu, sb, threadIdx.x & 31);
+  const int half = lp >> 4, l16 = lp & 15;
   const int la = l16 & 3, lb = l16 >> 2;
-  double* ebase = smem_l6 + (size_t)(2 * warp + half) * L6_EL;
+  const int warp = 0;                      // (only used through wid below)
+  double* ebase = reinterpret_cast<double*>(__cvta_shared_to_generic((size_t)sb));
   double* sq = ebase;                    // AoS landing zone of the element block, then the swizzled SoA q [5][64]
   double* sacc = ebase + L6_TILE;        // swizzled SoA running sums [5][64], handed from phase to phase
   double* tr = ebase + 2 * L6_TILE;      // face traces of the six neighbours
@@ -99,14 +121,14 @@ k_line6(const __grid_constant__ Dev d, const __grid_constant__ LineOps ops, doub
   const double gm1 = prm.gamma - 1;
   const int vflux = (VFLUX >= 0) ? VFLUX : d.vol_flux;
   const int sflux = (SFLUX >= 0) ? SFLUX : d.surf_flux;
-  const int64_t npairs = (count + 1) >> 1;
-  const int64_t wid = (int64_t)blockIdx.x * WARPS + warp, nw = (int64_t)gridDim.x * WARPS;
+  const int npairs = (int)((count + 1) >> 1);          // element ids are int (face_nbr), so pair indices fit
+  const int wid = blockIdx.x * WARPS + (threadIdx.x >> 5) + warp, nw = gridDim.x * WARPS;
 
-  auto elem_of = [&](int64_t pr, bool& valid) -> int {
-    int64_t s = 2 * pr + half;
-    valid = s < count;
-    if (!valid) s = count - 1;
-    return elems ? elems[s] : (int)s;
+  auto elem_of = [&](int pr, bool& valid) -> int {
+    int s = 2 * pr + half;
+    valid = s < (int)count;
+    if (!valid) s = (int)count - 1;
+    return elems ? elems[s] : s;
   };
   // neighbour codes of the two faces of direction dir (24 B per element, 8 B aligned)
   auto load_codes = [&](int el, int dir) -> int2 {
@@ -164,7 +186,7 @@ k_line6(const __grid_constant__ Dev d, const __grid_constant__ LineOps ops, doub
   const int Px = 16 * lb + 4 * (la ^ lb) + lb, Py = 20 * lb + (la ^ lb), Pz = l16;
 
   unsigned fbits = 0;
-  int64_t pr = wid;
+  int pr = wid;
   bool valid = false;
   int e = 0;
   // cp.async groups are committed in the order  z-traces, y-traces, block, x-traces  (of the NEXT pair): at the top
@@ -181,16 +203,16 @@ k_line6(const __grid_constant__ Dev d, const __grid_constant__ LineOps ops, doub
   }
 
   for (; pr < npairs; pr += nw) {
-    const int64_t pr_next = (pr + nw < npairs) ? pr + nw : pr;   // the last iteration prefetches its own element again
+    const int pr_next = (pr + nw < npairs) ? pr + nw : pr;   // the last iteration prefetches its own element again
     bool valid_next = false;
     const int e_next = elem_of(pr_next, valid_next);
     unsigned fbits_next = 0;
-    const double inv_jac = d.inv_jac[e];
+    asm volatile("prefetch.global.L1 [%0];" ::"l"(d.face_nbr + (size_t)e_next * 6));
 
     // ---- the block has landed: cons -> q in place. Lane (la, lb) reads the nodes (la, lb, m) = its z-line.
     cp_async_wait<1>();
     __syncwarp();
-    double Q[6][NV];   // virtual line nodes: low neighbour, nodes 0..3, high neighbour; slots (rho, vn/2, vt1/2, vt2/2, p)
+    double Q[6][NV];
     {
       double un[4][NV];
 #pragma unroll
@@ -205,8 +227,9 @@ k_line6(const __grid_constant__ Dev d, const __grid_constant__ LineOps ops, doub
         const int pos = Pz ^ (21 * m);
 #pragma unroll
         for (int v = 0; v < NV; ++v) sq[v * NN + pos] = q[v];
-        // z phase first: slot 1 = v3/2, then (v1/2, v2/2)
-        Q[1 + m][0] = q[0]; Q[1 + m][1] = q[3]; Q[1 + m][2] = q[1]; Q[1 + m][3] = q[2]; Q[1 + m][4] = q[4];
+        if (true) {   // z phase first: slot 1 = v3/2, then (v1/2, v2/2)
+          Q[1 + m][0] = q[0]; Q[1 + m][1] = q[3]; Q[1 + m][2] = q[1]; Q[1 + m][3] = q[2]; Q[1 + m][4] = q[4];
+        }
       }
     }
     __syncwarp();
@@ -217,24 +240,30 @@ k_line6(const __grid_constant__ Dev d, const __grid_constant__ LineOps ops, doub
       // rows of the velocity / momentum components in slot order (slot 1 = normal component)
       const int c0 = 1 + dir, c1 = (dir == 2) ? 1 : dir + 2, c2 = (dir == 0) ? 3 : dir;
       const int r0 = c0 * NN, r1 = c1 * NN, r2 = c2 * NN;
-      const int2 cn = load_codes(e_next, dir);   // issued early, consumed when the trace copies are issued
       const unsigned fb = fbits >> (4 * dir);
       const int P = dir == 0 ? Px : (dir == 1 ? Py : Pz);
       const int stp = dir == 0 ? 1 : (dir == 1 ? 4 : 21);
       const int pos[4] = {P, P ^ stp, P ^ (2 * stp), P ^ (3 * stp)};
+      double inv_jac = 0.0;
+      const int ec = e;
+      const bool valid_c = valid;
       if (step == 2) {
+        inv_jac = d.inv_jac[ec];    // needed when the first node is finished, half a phase from here
         cp_async_wait<2>();
         __syncwarp();
       }
+      // virtual line nodes: low neighbour, nodes 0..3, high neighbour; slots (rho, vn/2, vt1/2, vt2/2, p). Also the z
+      // phase re-reads its q (which its own lanes just wrote): a register copy carried into the loop would stay live
+      // across the back edge (40 registers) and push loop state into local memory.
       if (step > 0) {
 #pragma unroll
-        for (int m = 0; m < 4; ++m) {
-          Q[1 + m][0] = sq[pos[m]];
-          Q[1 + m][1] = sq[r0 + pos[m]];
-          Q[1 + m][2] = sq[r1 + pos[m]];
-          Q[1 + m][3] = sq[r2 + pos[m]];
-          Q[1 + m][4] = sq[4 * NN + pos[m]];
-        }
+      for (int m = 0; m < 4; ++m) {
+        Q[1 + m][0] = sq[pos[m]];
+        Q[1 + m][1] = sq[r0 + pos[m]];
+        Q[1 + m][2] = sq[r1 + pos[m]];
+        Q[1 + m][3] = sq[r2 + pos[m]];
+        Q[1 + m][4] = sq[4 * NN + pos[m]];
+      }
       }
       double nbv[2][NV];
 #pragma unroll
@@ -250,123 +279,132 @@ k_line6(const __grid_constant__ Dev d, const __grid_constant__ LineOps ops, doub
         cp_async_commit();
       }
       l3_to_q(nbv[0], gm1, Q[0]);
-      l3_to_q(nbv[1], gm1, Q[5]);
       const bool sfv_lo = SFV && (fb & 2u), sfv_hi = SFV && (fb & 8u);
 
-      // a finished node: step 0 starts the running sums, step 1 adds to them, step 2 adds, scales and keeps the result
-      auto hand_over = [&](int m, double* a) {
-        double* p = sacc + pos[m];
-        if (step == 0) {
-          p[0] = a[0]; p[r0] = a[1]; p[r1] = a[2]; p[r2] = a[3]; p[4 * NN] = a[4];
-        } else if (step == 1) {
-          p[0] += a[0]; p[r0] += a[1]; p[r1] += a[2]; p[r2] += a[3]; p[4 * NN] += a[4];
+      // Running sums of the earlier phases. The tile keeps them in the SLOT order of the phase that wrote them (static
+      // rows); with the phases running z, y, x a phase's slot 1 + s is the previous phase's slot 1 + (s + 2) % 3. They
+      // are the initial values of this phase's sums (no separate add), loaded early; the phase's result goes back to
+      // the same entries in its own slot order (each lane touches only its own nodes).
+      auto load_old = [&](int m, double* a) {
+        const double* p = sacc + pos[m];
+        if (step > 0) {
+          a[0] = p[0]; a[1] = p[3 * NN]; a[2] = p[1 * NN]; a[3] = p[2 * NN]; a[4] = p[4 * NN];
         } else {
-          // x phase: slots are (x, y, z) = the natural component order
-          a[0] = (a[0] + p[0]) * -inv_jac;
-          a[1] = (a[1] + p[1 * NN]) * -inv_jac;
-          a[2] = (a[2] + p[2 * NN]) * -inv_jac;
-          a[3] = (a[3] + p[3 * NN]) * -inv_jac;
-          a[4] = (a[4] + p[4 * NN]) * -inv_jac;
+#pragma unroll
+          for (int v = 0; v < NV; ++v) a[v] = 0.0;
+        }
+      };
+      // a finished node: handed to the next phase, or (x phase) scaled by the Jacobian (+ source terms)
+      auto hand_over = [&](int m, double* a) {
+        if (step < 2) {
+          double* p = sacc + pos[m];
+#pragma unroll
+          for (int v = 0; v < NV; ++v) p[v * NN] = a[v];
+        } else {
+#pragma unroll
+          for (int v = 0; v < NV; ++v) a[v] *= -inv_jac;
           if (d.src != TRIXIB200_SRC_NONE) {
-            const L3Vec5 sv = l3_source(&d, e, m + 4 * l16, m, la, lb, inv_jac, t, u);
+            const L3Vec5 sv = l3_source(&d, ec, m + 4 * l16, m, la, lb, inv_jac, t, u);
 #pragma unroll
             for (int v = 0; v < NV; ++v) a[v] += sv.v[v];
           }
         }
       };
 
-      // ---- batch A: (lo,0), (0,1), (0,2), (0,3)  (reference dg_3d_kernel.jl:188-257 evaluates 12 volume fluxes per
-      // node, and the interface fluxes in two more kernels)
-      double acc0[NV], acc1[NV], acc2[NV], acc3[NV];
-      {
-        double F[4][NV];
-        unsigned rough = l6_flux4<FAST, 0, 1, 1, 2, 1, 3, 1, 4>(Q, sflux, vflux, vflux, vflux, prm, F);
-        if (SFV) {
+      // ---- the 8 pair fluxes of the line in batches of NP (reference dg_3d_kernel.jl:188-257 evaluates 12 volume
+      // fluxes per node, and the interface fluxes in two more kernels); a node is handed over as soon as its last pair
+      // is in: node 0 after pair 3, node 1 after pair 5, nodes 2 and 3 after pair 7
+      double acc[4][NV];
+      load_old(0, acc[0]);
+      auto batch = [&](auto k0_tag) {
+        constexpr int K0 = decltype(k0_tag)::value;
+        if (K0 + NP > 7) l3_to_q(nbv[1], gm1, Q[5]);   // converted when its pair comes up
+        double F[NP][NV];
+        unsigned rough = l6_fluxes<FAST, K0, NP>(Q, vflux, sflux, prm, F);
+        if (SFV && K0 == 0) {
           if (sfv_lo) rough &= ~1u;
 #pragma unroll
           for (int v = 0; v < NV; ++v) F[0][v] = sfv_lo ? nbv[0][v] : F[0][v];
         }
+        if (SFV && K0 + NP > 7) {
+          if (sfv_hi) rough &= ~(1u << (7 - K0));
 #pragma unroll
-        for (int v = 0; v < NV; ++v) {
-          acc0[v] = fma(ops.ds[0 + 4 * 3], F[3][v], fma(ops.ds[0 + 4 * 2], F[2][v], fma(ops.ds[0 + 4 * 1], F[1][v], -ops.factor_1 * F[0][v])));
-          acc1[v] = ops.ds[1 + 4 * 0] * F[1][v];
-          acc2[v] = ops.ds[2 + 4 * 0] * F[2][v];
-          acc3[v] = ops.ds[3 + 4 * 0] * F[3][v];
+          for (int v = 0; v < NV; ++v) F[7 - K0][v] = sfv_hi ? nbv[1][v] : F[7 - K0][v];
         }
+        if (K0 <= 1 && K0 + NP > 1) load_old(1, acc[1]);
+        if (K0 <= 2 && K0 + NP > 2) load_old(2, acc[2]);
+        if (K0 <= 3 && K0 + NP > 3) load_old(3, acc[3]);
+        auto accumulate = [&](int k, int v) {
+          const int kk = K0 + k;
+          if (kk == 0) acc[0][v] = fma(-ops.factor_1, F[k][v], acc[0][v]);
+          else if (kk == 7) acc[3][v] = fma(ops.factor_2, F[k][v], acc[3][v]);
+          else {
+            const int x = L6_PA[kk] - 1, y = L6_PB[kk] - 1;
+            acc[x][v] = fma(ops.ds[x + 4 * y], F[k][v], acc[x][v]);
+            acc[y][v] = fma(ops.ds[y + 4 * x], F[k][v], acc[y][v]);
+          }
+        };
+#pragma unroll
+        for (int k = 0; k < NP; ++k)
+#pragma unroll
+          for (int v = 0; v < NV; ++v) accumulate(k, v);
         if (FAST && rough != 0) {
 #pragma unroll
-          for (int k = 0; k < 4; ++k)
+          for (int k = 0; k < NP; ++k)
             if (rough & (1u << k)) {
+              const int kk = K0 + k;
               L6Pair pp;
 #pragma unroll
-              for (int v = 0; v < NV; ++v) { pp.a[v] = Q[k == 0 ? 0 : 1][v]; pp.b[v] = Q[k == 0 ? 1 : 1 + k][v]; }
+              for (int v = 0; v < NV; ++v) { pp.a[v] = Q[L6_PA[kk]][v]; pp.b[v] = Q[L6_PB[kk]][v]; }
               const L3Vec5 df = l6_pair_correction(pp, prm.inv_gm1);
 #pragma unroll
               for (int v = 0; v < NV; ++v) {
-                if (k == 0) acc0[v] = fma(-ops.factor_1, df.v[v], acc0[v]);
-                else acc0[v] = fma(ops.ds[0 + 4 * k], df.v[v], acc0[v]);
-                if (k == 1) acc1[v] = fma(ops.ds[1], df.v[v], acc1[v]);
-                if (k == 2) acc2[v] = fma(ops.ds[2], df.v[v], acc2[v]);
-                if (k == 3) acc3[v] = fma(ops.ds[3], df.v[v], acc3[v]);
+                if (kk == 0) acc[0][v] = fma(-ops.factor_1, df.v[v], acc[0][v]);
+                else if (kk == 7) acc[3][v] = fma(ops.factor_2, df.v[v], acc[3][v]);
+                else {
+                  const int x = L6_PA[kk] - 1, y = L6_PB[kk] - 1;
+                  acc[x][v] = fma(ops.ds[x + 4 * y], df.v[v], acc[x][v]);
+                  acc[y][v] = fma(ops.ds[y + 4 * x], df.v[v], acc[y][v]);
+                }
               }
             }
         }
-      }
-      hand_over(0, acc0);
-      if (step == 2 && valid) {
-        double2* o = reinterpret_cast<double2*>(du + (size_t)NV * NN * e + 20 * l16);
-        o[0] = make_double2(acc0[0], acc0[1]);
-        o[1] = make_double2(acc0[2], acc0[3]);
-      }
-      // ---- batch B: (1,2), (1,3), (2,3), (3,hi)
-      {
-        double F[4][NV];
-        unsigned rough = l6_flux4<FAST, 2, 3, 2, 4, 3, 4, 4, 5>(Q, vflux, vflux, vflux, sflux, prm, F);
-        if (SFV) {
-          if (sfv_hi) rough &= ~8u;
-#pragma unroll
-          for (int v = 0; v < NV; ++v) F[3][v] = sfv_hi ? nbv[1][v] : F[3][v];
+        // finished nodes
+        if (K0 <= 3 && K0 + NP > 3) {
+          hand_over(0, acc[0]);
+          if (step == 2 && valid_c) {
+            double2* o = reinterpret_cast<double2*>(du + (size_t)NV * NN * ec + 20 * l16);
+            __stcs(&o[0], make_double2(acc[0][0], acc[0][1]));
+            __stcs(&o[1], make_double2(acc[0][2], acc[0][3]));
+          }
         }
-#pragma unroll
-        for (int v = 0; v < NV; ++v) {
-          acc1[v] = fma(ops.ds[1 + 4 * 3], F[1][v], fma(ops.ds[1 + 4 * 2], F[0][v], acc1[v]));
-          acc2[v] = fma(ops.ds[2 + 4 * 3], F[2][v], fma(ops.ds[2 + 4 * 1], F[0][v], acc2[v]));
-          acc3[v] = fma(ops.factor_2, F[3][v], fma(ops.ds[3 + 4 * 2], F[2][v], fma(ops.ds[3 + 4 * 1], F[1][v], acc3[v])));
+        if (K0 <= 5 && K0 + NP > 5) {
+          hand_over(1, acc[1]);
+          if (step == 2 && valid_c) {
+            double2* o = reinterpret_cast<double2*>(du + (size_t)NV * NN * ec + 20 * l16);
+            __stcs(&o[2], make_double2(acc[0][4], acc[1][0]));
+            __stcs(&o[3], make_double2(acc[1][1], acc[1][2]));
+            __stcs(&o[4], make_double2(acc[1][3], acc[1][4]));
+          }
         }
-        if (FAST && rough != 0) {
-#pragma unroll
-          for (int k = 0; k < 4; ++k)
-            if (rough & (1u << k)) {
-              constexpr int XA[4] = {2, 2, 3, 4}, XB[4] = {3, 4, 4, 5};
-              L6Pair pp;
-#pragma unroll
-              for (int v = 0; v < NV; ++v) { pp.a[v] = Q[XA[k]][v]; pp.b[v] = Q[XB[k]][v]; }
-              const L3Vec5 df = l6_pair_correction(pp, prm.inv_gm1);
-#pragma unroll
-              for (int v = 0; v < NV; ++v) {
-                if (k == 0) { acc1[v] = fma(ops.ds[1 + 4 * 2], df.v[v], acc1[v]); acc2[v] = fma(ops.ds[2 + 4 * 1], df.v[v], acc2[v]); }
-                if (k == 1) { acc1[v] = fma(ops.ds[1 + 4 * 3], df.v[v], acc1[v]); acc3[v] = fma(ops.ds[3 + 4 * 1], df.v[v], acc3[v]); }
-                if (k == 2) { acc2[v] = fma(ops.ds[2 + 4 * 3], df.v[v], acc2[v]); acc3[v] = fma(ops.ds[3 + 4 * 2], df.v[v], acc3[v]); }
-                if (k == 3) acc3[v] = fma(ops.factor_2, df.v[v], acc3[v]);
-              }
-            }
+        if (K0 + NP > 7) {
+          hand_over(2, acc[2]);
+          hand_over(3, acc[3]);
+          if (step == 2 && valid_c) {
+            double2* o = reinterpret_cast<double2*>(du + (size_t)NV * NN * ec + 20 * l16);
+            __stcs(&o[5], make_double2(acc[2][0], acc[2][1]));
+            __stcs(&o[6], make_double2(acc[2][2], acc[2][3]));
+            __stcs(&o[7], make_double2(acc[2][4], acc[3][0]));
+            __stcs(&o[8], make_double2(acc[3][1], acc[3][2]));
+            __stcs(&o[9], make_double2(acc[3][3], acc[3][4]));
+          }
         }
-      }
-      hand_over(1, acc1);
-      hand_over(2, acc2);
-      hand_over(3, acc3);
-      if (step == 2 && valid) {
-        double2* o = reinterpret_cast<double2*>(du + (size_t)NV * NN * e + 20 * l16);
-        o[2] = make_double2(acc0[4], acc1[0]);
-        o[3] = make_double2(acc1[1], acc1[2]);
-        o[4] = make_double2(acc1[3], acc1[4]);
-        o[5] = make_double2(acc2[0], acc2[1]);
-        o[6] = make_double2(acc2[2], acc2[3]);
-        o[7] = make_double2(acc2[4], acc3[0]);
-        o[8] = make_double2(acc3[1], acc3[2]);
-        o[9] = make_double2(acc3[3], acc3[4]);
-      }
+      };
+      batch(std::integral_constant<int, 0>{});
+      if (NP <= 4) batch(std::integral_constant<int, NP>{});
+      if (NP <= 2) { batch(std::integral_constant<int, 2 * NP>{}); batch(std::integral_constant<int, 3 * NP>{}); }
       __syncwarp();   // traces consumed, running sums visible
+      const int2 cn = load_codes(e_next, dir);   // L1 hit: the line was prefetched at the top of the iteration
       if (dir == 0) issue_traces(D0{}, e_next, cn.x, cn.y);
       else if (dir == 1) issue_traces(D1{}, e_next, cn.x, cn.y);
       else issue_traces(D2{}, e_next, cn.x, cn.y);
@@ -379,11 +417,15 @@ k_line6(const __grid_constant__ Dev d, const __grid_constant__ LineOps ops, doub
 }
 
 // ---------------------------------------------------------------------------------------------- host side
-template <int VFLUX, int SFLUX, bool SFV, int CTAS = 3>
+// Launch shapes. Measured on B200 at level 7 (profiles/r1_line6_shapes.txt): 2 CTAs x 4 warps with all 8 pairs staged
+// (<= 255 registers) 4.75 ms, batches of 4 / 2 pairs 4.87 / 4.89 ms; 3 CTAs x 4 warps (168 registers) 4.87 ms with
+// batches of 2 and 5.3 ms with batches of 4 (local-memory spills of loop state, each reload an L2 round trip). The
+// kernel's time follows the SUM of the issue costs of its instructions, not the occupancy: 1 warp per scheduler already
+// reaches 70 % of the throughput of 2, and 3 add nothing (profiles/r1_line6_notes.md).
+template <int VFLUX, int SFLUX, bool SFV, int CTAS, int WARPS, int NP>
 static int line6_launch_t(const Dev& d, const LineOps& ops, double* du, const double* u, double t, const int* elems,
                           int64_t count, cudaStream_t stream, int sm_count) {
-  constexpr int WARPS = 4;
-  auto kern = k_line6<VFLUX, SFLUX, SFV, WARPS, CTAS>;
+  auto kern = k_line6<VFLUX, SFLUX, SFV, WARPS, CTAS, NP>;
   static bool configured = false;
   if (!configured) {
     if (cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)l6_smem(WARPS)) != cudaSuccess)
@@ -403,14 +445,14 @@ static int line6_launch(const trixib200_config& c, const Dev& d, const LineOps& 
                         double t, const int* elems, int64_t count, cudaStream_t s, int sm_count) {
   constexpr int R = TRIXIB200_FLUX_RANOCHA;
   const bool sfv = d.B > 0 || d.M > 0;   // faces whose flux is given in surface_flux_values (boundaries, mortars)
-  // TRIXIB200_LINE_CTAS=2: the same code at 2 CTAs (8 warps) per SM and up to 255 registers (A/B measurements)
-  static const bool two = getenv("TRIXIB200_LINE_CTAS") && atoi(getenv("TRIXIB200_LINE_CTAS")) == 2;
-  if (two && !sfv && c.volume_flux == R && c.surface_flux == R)
-    return line6_launch_t<R, R, false, 2>(d, ops, du, u, t, elems, count, s, sm_count);
-  if (c.volume_flux == R && c.surface_flux == R)
-    return sfv ? line6_launch_t<R, R, true>(d, ops, du, u, t, elems, count, s, sm_count)
-               : line6_launch_t<R, R, false>(d, ops, du, u, t, elems, count, s, sm_count);
-  return line6_launch_t<-1, -1, true>(d, ops, du, u, t, elems, count, s, sm_count);
+  if (c.volume_flux == R && c.surface_flux == R) {
+    // TRIXIB200_LINE_SHAPE=3: 3 CTAs x 4 warps per SM at 168 registers, batches of 2 pairs (A/B measurements)
+    static const bool three = getenv("TRIXIB200_LINE_SHAPE") && atoi(getenv("TRIXIB200_LINE_SHAPE")) == 3;
+    if (three && !sfv) return line6_launch_t<R, R, false, 3, 4, 2>(d, ops, du, u, t, elems, count, s, sm_count);
+    return sfv ? line6_launch_t<R, R, true, 2, 4, 8>(d, ops, du, u, t, elems, count, s, sm_count)
+               : line6_launch_t<R, R, false, 2, 4, 8>(d, ops, du, u, t, elems, count, s, sm_count);
+  }
+  return line6_launch_t<-1, -1, true, 2, 4, 2>(d, ops, du, u, t, elems, count, s, sm_count);
 }
 
 }  // namespace tb
