@@ -207,7 +207,7 @@ k_line6(const __grid_constant__ Dev d, const __grid_constant__ LineOps ops, doub
     bool valid_next = false;
     const int e_next = elem_of(pr_next, valid_next);
     unsigned fbits_next = 0;
-    asm volatile("prefetch.global.L1 [%0];" ::"l"(d.face_nbr + (size_t)e_next * 6));
+    const double inv_jac = d.inv_jac[e];
 
     // ---- the block has landed: cons -> q in place. Lane (la, lb) reads the nodes (la, lb, m) = its z-line.
     cp_async_wait<1>();
@@ -240,21 +240,19 @@ k_line6(const __grid_constant__ Dev d, const __grid_constant__ LineOps ops, doub
       // rows of the velocity / momentum components in slot order (slot 1 = normal component)
       const int c0 = 1 + dir, c1 = (dir == 2) ? 1 : dir + 2, c2 = (dir == 0) ? 3 : dir;
       const int r0 = c0 * NN, r1 = c1 * NN, r2 = c2 * NN;
+      const int2 cn = load_codes(e_next, dir);   // issued early, consumed when the trace copies are issued
       const unsigned fb = fbits >> (4 * dir);
       const int P = dir == 0 ? Px : (dir == 1 ? Py : Pz);
       const int stp = dir == 0 ? 1 : (dir == 1 ? 4 : 21);
       const int pos[4] = {P, P ^ stp, P ^ (2 * stp), P ^ (3 * stp)};
-      double inv_jac = 0.0;
       const int ec = e;
       const bool valid_c = valid;
       if (step == 2) {
-        inv_jac = d.inv_jac[ec];    // needed when the first node is finished, half a phase from here
         cp_async_wait<2>();
         __syncwarp();
       }
-      // virtual line nodes: low neighbour, nodes 0..3, high neighbour; slots (rho, vn/2, vt1/2, vt2/2, p). Also the z
-      // phase re-reads its q (which its own lanes just wrote): a register copy carried into the loop would stay live
-      // across the back edge (40 registers) and push loop state into local memory.
+      // virtual line nodes: low neighbour, nodes 0..3, high neighbour; slots (rho, vn/2, vt1/2, vt2/2, p); the z phase
+      // still has its q in registers from the conversion
       if (step > 0) {
 #pragma unroll
       for (int m = 0; m < 4; ++m) {
@@ -404,7 +402,6 @@ k_line6(const __grid_constant__ Dev d, const __grid_constant__ LineOps ops, doub
       if (NP <= 4) batch(std::integral_constant<int, NP>{});
       if (NP <= 2) { batch(std::integral_constant<int, 2 * NP>{}); batch(std::integral_constant<int, 3 * NP>{}); }
       __syncwarp();   // traces consumed, running sums visible
-      const int2 cn = load_codes(e_next, dir);   // L1 hit: the line was prefetched at the top of the iteration
       if (dir == 0) issue_traces(D0{}, e_next, cn.x, cn.y);
       else if (dir == 1) issue_traces(D1{}, e_next, cn.x, cn.y);
       else issue_traces(D2{}, e_next, cn.x, cn.y);
