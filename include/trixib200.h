@@ -174,6 +174,20 @@ int trixib200_fill_initial_condition(trixib200_handle* h, double* u, double t);
 int trixib200_rk2n_update(trixib200_handle* h, double* u, double* tmp, const double* du, double a, double b,
                           double dt);
 
+/* rhs! fused with one 2N low-storage Runge-Kutta stage (the caller is OrdinaryDiffEq's
+ * `perform_step!` for `CarpenterKennedy2N54`, outside the reference, whose stage is `rhs_gpu!` (reference
+ * src/solvers/solvers.jl:18-31) followed by two broadcasts):
+ *     tmp = a * tmp + dt * rhs(u_in, t);   u_out = u_in + b * tmp
+ * On the line-owner kernel path this is ONE launch and du is never written to memory (160 instead of 280 B/DOF of HBM
+ * traffic per stage); other kernel families run rhs! into a library-owned scratch vector followed by one update
+ * kernel. u_out must not alias u_in. tmp is not read when a == 0 (first stage). Device pointers, asynchronous. */
+int trixib200_rk2n_stage(trixib200_handle* h, double* u_out, const double* u_in, double* tmp, double t, double a,
+                         double b, double dt);
+/* one full CarpenterKennedy2N54 step t -> t + dt (five fused stages ping-ponging between u and u_alt); the result
+ * is in u_alt iff *result_in_alt == 1 (five stages: it is) */
+int trixib200_rk2n_step_ck54(trixib200_handle* h, double* u, double* u_alt, double* tmp, double t, double dt,
+                             int* result_in_alt);
+
 /* timing helpers: run rhs `reps` times back to back and return the elapsed device time in milliseconds,
  * measured with CUDA events on the handle's stream */
 int trixib200_time_rhs(trixib200_handle* h, double* du, const double* u, double t, int reps, float* ms_out);

@@ -178,6 +178,56 @@ def test_full_run_error_norms(name, tend, cfl):
     assert rel_max_err(sol.u[-1].cpu().numpy(), u_ref) <= 1e-10
 
 
+@pytest.mark.parametrize("name", ["c5_euler_ec_3d", "euler_shima_3d", "euler_ec_mortar_3d", "euler_fd_nonperiodic_3d",
+                                  "c2_euler_ec_2d", "c4_mhd_alfven_mortar_3d", "c1_advection_1d"])
+def test_rk2n_stage_matches_rhs_plus_update(name):
+    """trixib200_rk2n_stage (rhs! fused with the 2N Runge-Kutta stage; one launch on the line-owner path, scratch du +
+    update kernel elsewhere) against the oracle's du and the textbook update, for a first stage (a = 0, tmp unread)
+    and a later one."""
+    c = CASES[name]
+    o, semi = make_oracle(c), make_semi(c)
+    torch = _torch()
+    u = o.compute_coefficients(0.0)
+    t, dt = 0.2, 1.7e-3
+    du_ref = o.rhs(u, t)
+    rng = np.random.default_rng(3)
+    tmp0 = rng.standard_normal(u.size)
+    for a, b in ((0.0, 0.1496590219993), (-0.4178904745, 0.3792103129999)):
+        u_in = _to_dev(semi, u)
+        u_out = semi.new_vector().fill_(float("nan"))
+        tmp = _to_dev(semi, tmp0) if a != 0.0 else semi.new_vector().fill_(float("nan"))
+        l0 = semi.launch_count()
+        semi.rk2n_stage(u_out, u_in, tmp, t, a, b, dt)
+        torch.cuda.synchronize()
+        if semi.line3d and semi.size("nboundaries") + semi.size("nmortars") == 0:
+            assert semi.launch_count() - l0 == 1                    # rhs! + update in ONE launch
+        tmp_ref = (a * tmp0 if a != 0.0 else 0.0) + dt * du_ref
+        u_ref = u + b * tmp_ref
+        assert np.abs(tmp.cpu().numpy() - tmp_ref).max() <= TOL * dt * np.abs(du_ref).max() + 1e-15 * np.abs(tmp_ref).max()
+        assert np.abs(u_out.cpu().numpy() - u_ref).max() <= TOL * dt * np.abs(du_ref).max() + 4e-16 * np.abs(u_ref).max()
+        assert torch.equal(u_in.cpu(), torch.from_numpy(u))          # u_in untouched
+    with pytest.raises(Exception):
+        semi.rk2n_stage(u_in, u_in, tmp, t, 0.0, 1.0, dt)             # aliasing is rejected
+
+
+@pytest.mark.parametrize("name,tend,cfl", [("c5_euler_ec_3d", 0.1, 1.3), ("c2_euler_ec_2d", 0.1, 1.0)])
+def test_full_run_with_fused_rk_stages(name, tend, cfl):
+    """The same full run as test_full_run_error_norms with every stage as one fused call."""
+    import trixib200 as T
+    c = CASES[name]
+    o, semi = make_oracle(c), make_semi(c)
+    u_ref, steps_ref = o.solve(o.compute_coefficients(0.0), 0.0, tend, cfl=cfl)
+    l2_ref, linf_ref = o.error_norms(u_ref, tend)
+    ode = T.semidiscretizeGPU(semi, (0.0, tend))
+    ana = T.AnalysisCallback(semi)
+    sol = T.solve(ode, T.CarpenterKennedy2N54(), callback=T.CallbackSet(ana, T.StepsizeCallback(cfl=cfl)),
+                  fused_stages=True)
+    assert sol.nsteps == steps_ref
+    _, l2, linf = ana.history[-1]
+    assert np.abs(l2 - l2_ref).max() <= 1e-10 and np.abs(linf - linf_ref).max() <= 1e-10
+    assert rel_max_err(sol.u[-1].cpu().numpy(), u_ref) <= 1e-10
+
+
 def test_large_mesh_properties():
     """Size-independent properties at a size the oracle would not finish in seconds (3D Euler EC, level 5,
     2.1 M DOF): free-stream preservation, discrete conservation and entropy conservation of the EC scheme."""

@@ -62,7 +62,8 @@ EXPORTS = [
     "trixib200_last_error", "trixib200_version", "trixib200_create", "trixib200_destroy", "trixib200_size",
     "trixib200_rhs", "trixib200_max_dt", "trixib200_stage", "trixib200_cache_len", "trixib200_cache_get",
     "trixib200_alloc", "trixib200_free", "trixib200_upload", "trixib200_download", "trixib200_sync",
-    "trixib200_stream", "trixib200_fill_initial_condition", "trixib200_rk2n_update", "trixib200_time_rhs",
+    "trixib200_stream", "trixib200_fill_initial_condition", "trixib200_rk2n_update", "trixib200_rk2n_stage", "trixib200_rk2n_step_ck54",
+    "trixib200_time_rhs",
     "trixib200_launch_count", "trixib200_comm_unique_id", "trixib200_comm_init", "trixib200_set_stream",
     "trixib200_rhs_host", "trixib200_host_register", "trixib200_host_unregister",
     "trixib200_plan_create", "trixib200_plan_destroy", "trixib200_plan_len", "trixib200_plan_get",
@@ -130,6 +131,10 @@ def lib():
     L.trixib200_fill_initial_condition.argtypes = [C.c_void_p, C.c_void_p, C.c_double]
     L.trixib200_rk2n_update.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_double, C.c_double,
                                         C.c_double]
+    L.trixib200_rk2n_stage.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_double, C.c_double,
+                                       C.c_double, C.c_double]
+    L.trixib200_rk2n_step_ck54.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_double, C.c_double,
+                                           C.POINTER(C.c_int)]
     L.trixib200_time_rhs.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_double, C.c_int,
                                      C.POINTER(C.c_float)]
     L.trixib200_launch_count.restype = C.c_int64

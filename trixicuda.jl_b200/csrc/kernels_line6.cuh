@@ -88,16 +88,31 @@ TB_D unsigned l6_fluxes(const double (&Q)[6][5], int vflux, int sflux, const EqP
   return rough;
 }
 
+// Fused low-storage Runge-Kutta stage (2N scheme, e.g. CarpenterKennedy2N54): instead of writing du the x phase does
+//   tmp = a * tmp + dt * du;   u_out = u_in + b * tmp
+// on the 20 contiguous doubles every lane holds, so du never exists in memory and the separate update sweep (read du,
+// tmp, u; write tmp, u: 200 B/DOF) disappears. u_out must not alias u_in (neighbours still read u_in).
+struct RkArgs {
+  double* tmp;       // [nunknowns] the 2N register; not read when a == 0 (first stage)
+  double a, b, dt;
+};
+
 // registers per thread that let CTAS CTAs of WARPS warps share the 64 K registers of an SM (allocation unit: 8 per thread)
 constexpr int l6_maxnreg(int warps, int ctas) {
   const int r = (65536 / (32 * warps * ctas)) / 8 * 8;
   return r > 255 ? 255 : r;
 }
 
-template <int VFLUX, int SFLUX, bool SFV, int WARPS, int CTAS, int NP>
+template <int VFLUX, int SFLUX, bool SFV, int WARPS, int CTAS, int NP, bool RK = false, bool TOUT = false>
 __global__ void __launch_bounds__(32 * WARPS) __maxnreg__(l6_maxnreg(WARPS, CTAS))
 k_line6(const __grid_constant__ Dev d, const __grid_constant__ LineOps ops, double* __restrict__ du,
-        const double* __restrict__ u, double t, const int* __restrict__ elems, int64_t count) {
+        const double* __restrict__ u, double t, const int* __restrict__ elems, int64_t count,
+        const __grid_constant__ RkArgs rk) {
+  // TILE: the x phase parks its 20 doubles per lane in a padded shared tile and a second pass moves whole 16-byte
+  // chunks l16 + 16 m, i.e. fully coalesced global accesses. A 16-byte access per lane at a 160-byte stride touches
+  // ~40 cache lines per warp instruction and makes the L1 the bottleneck of the fused RK stage (7.6 vs 5.8 ms at
+  // level 7); for the plain du store the tile is worth 1 % (profiles/r1_line6_notes.md).
+  constexpr bool TILE = RK || TOUT;
   constexpr int NV = 5, NN = 64;
   constexpr bool FAST = (VFLUX == TRIXIB200_FLUX_RANOCHA && SFLUX == TRIXIB200_FLUX_RANOCHA);
   extern __shared__ __align__(16) double smem_l6[];
@@ -299,15 +314,29 @@ k_line6(const __grid_constant__ Dev d, const __grid_constant__ LineOps ops, doub
 #pragma unroll
           for (int v = 0; v < NV; ++v) p[v * NN] = a[v];
         } else {
+          const double scale = RK ? -inv_jac * rk.dt : -inv_jac;
 #pragma unroll
-          for (int v = 0; v < NV; ++v) a[v] *= -inv_jac;
+          for (int v = 0; v < NV; ++v) a[v] *= scale;
           if (d.src != TRIXIB200_SRC_NONE) {
             const L3Vec5 sv = l3_source(&d, ec, m + 4 * l16, m, la, lb, inv_jac, t, u);
 #pragma unroll
-            for (int v = 0; v < NV; ++v) a[v] += sv.v[v];
+            for (int v = 0; v < NV; ++v) a[v] = RK ? fma(rk.dt, sv.v[v], a[v]) : a[v] + sv.v[v];
           }
         }
       };
+      if (RK && step == 1) {
+        // one phase ahead: pull the 20 + 20 lines of the element's old tmp / u_in into L1, so that the two fetches of
+        // the x phase are L1 hits (tmp comes from DRAM, u_in from L2: it was read through cp.async three phases ago)
+        const char* bu = reinterpret_cast<const char*>(u + (size_t)NV * NN * ec);
+        const char* bt = reinterpret_cast<const char*>(rk.tmp + (size_t)NV * NN * ec);
+        asm volatile("prefetch.global.L1 [%0];" ::"l"(bu + 128 * l16));
+        if (rk.a != 0.0) asm volatile("prefetch.global.L1 [%0];" ::"l"(bt + 128 * l16));
+        if (l16 < 4) {
+          asm volatile("prefetch.global.L1 [%0];" ::"l"(bu + 128 * (16 + l16)));
+          if (rk.a != 0.0) asm volatile("prefetch.global.L1 [%0];" ::"l"(bt + 128 * (16 + l16)));
+        }
+      }
+      double2* xt = reinterpret_cast<double2*>(sacc) + 11 * l16;   // TILE: this lane's row (10 chunks, stride 11)
 
       // ---- the 8 pair fluxes of the line in batches of NP (reference dg_3d_kernel.jl:188-257 evaluates 12 volume
       // fluxes per node, and the interface fluxes in two more kernels); a node is handed over as soon as its last pair
@@ -370,37 +399,92 @@ k_line6(const __grid_constant__ Dev d, const __grid_constant__ LineOps ops, doub
         // finished nodes
         if (K0 <= 3 && K0 + NP > 3) {
           hand_over(0, acc[0]);
-          if (step == 2 && valid_c) {
-            double2* o = reinterpret_cast<double2*>(du + (size_t)NV * NN * ec + 20 * l16);
-            __stcs(&o[0], make_double2(acc[0][0], acc[0][1]));
-            __stcs(&o[1], make_double2(acc[0][2], acc[0][3]));
+          if (step == 2) {
+            if (TILE) {
+              __syncwarp();      // every lane has taken its running sums out of the tile region
+              xt[0] = make_double2(acc[0][0], acc[0][1]);
+              xt[1] = make_double2(acc[0][2], acc[0][3]);
+            } else if (valid_c) {
+              double2* o = reinterpret_cast<double2*>(du + (size_t)NV * NN * ec + 20 * l16);
+              __stcs(&o[0], make_double2(acc[0][0], acc[0][1]));
+              __stcs(&o[1], make_double2(acc[0][2], acc[0][3]));
+            }
           }
         }
         if (K0 <= 5 && K0 + NP > 5) {
           hand_over(1, acc[1]);
-          if (step == 2 && valid_c) {
-            double2* o = reinterpret_cast<double2*>(du + (size_t)NV * NN * ec + 20 * l16);
-            __stcs(&o[2], make_double2(acc[0][4], acc[1][0]));
-            __stcs(&o[3], make_double2(acc[1][1], acc[1][2]));
-            __stcs(&o[4], make_double2(acc[1][3], acc[1][4]));
+          if (step == 2) {
+            if (TILE) {
+              xt[2] = make_double2(acc[0][4], acc[1][0]);
+              xt[3] = make_double2(acc[1][1], acc[1][2]);
+              xt[4] = make_double2(acc[1][3], acc[1][4]);
+            } else if (valid_c) {
+              double2* o = reinterpret_cast<double2*>(du + (size_t)NV * NN * ec + 20 * l16);
+              __stcs(&o[2], make_double2(acc[0][4], acc[1][0]));
+              __stcs(&o[3], make_double2(acc[1][1], acc[1][2]));
+              __stcs(&o[4], make_double2(acc[1][3], acc[1][4]));
+            }
           }
         }
         if (K0 + NP > 7) {
           hand_over(2, acc[2]);
           hand_over(3, acc[3]);
-          if (step == 2 && valid_c) {
-            double2* o = reinterpret_cast<double2*>(du + (size_t)NV * NN * ec + 20 * l16);
-            __stcs(&o[5], make_double2(acc[2][0], acc[2][1]));
-            __stcs(&o[6], make_double2(acc[2][2], acc[2][3]));
-            __stcs(&o[7], make_double2(acc[2][4], acc[3][0]));
-            __stcs(&o[8], make_double2(acc[3][1], acc[3][2]));
-            __stcs(&o[9], make_double2(acc[3][3], acc[3][4]));
+          if (step == 2) {
+            if (TILE) {
+              xt[5] = make_double2(acc[2][0], acc[2][1]);
+              xt[6] = make_double2(acc[2][2], acc[2][3]);
+              xt[7] = make_double2(acc[2][4], acc[3][0]);
+              xt[8] = make_double2(acc[3][1], acc[3][2]);
+              xt[9] = make_double2(acc[3][3], acc[3][4]);
+            } else if (valid_c) {
+              double2* o = reinterpret_cast<double2*>(du + (size_t)NV * NN * ec + 20 * l16);
+              __stcs(&o[5], make_double2(acc[2][0], acc[2][1]));
+              __stcs(&o[6], make_double2(acc[2][2], acc[2][3]));
+              __stcs(&o[7], make_double2(acc[2][4], acc[3][0]));
+              __stcs(&o[8], make_double2(acc[3][1], acc[3][2]));
+              __stcs(&o[9], make_double2(acc[3][3], acc[3][4]));
+            }
           }
         }
       };
       batch(std::integral_constant<int, 0>{});
-      if (NP <= 4) batch(std::integral_constant<int, NP>{});
-      if (NP <= 2) { batch(std::integral_constant<int, 2 * NP>{}); batch(std::integral_constant<int, 3 * NP>{}); }
+      if constexpr (NP <= 4) batch(std::integral_constant<int, NP>{});
+      if constexpr (NP <= 2) { batch(std::integral_constant<int, 2 * NP>{}); batch(std::integral_constant<int, 3 * NP>{}); }
+      if (TILE && step == 2) {
+        // second pass over whole 16-byte chunks c = l16 + 16 j of the element block (tile position c + c / 10):
+        // plain du store, or the 2N Runge-Kutta stage  tmp = a tmp + dt du;  u_out = u_in + b tmp
+        __syncwarp();
+        const double2* tile = reinterpret_cast<const double2*>(sacc);
+        double2* po = reinterpret_cast<double2*>(du + (size_t)NV * NN * ec);
+        double2* pt = RK ? reinterpret_cast<double2*>(rk.tmp + (size_t)NV * NN * ec) : nullptr;
+        const double2* pu = reinterpret_cast<const double2*>(u + (size_t)NV * NN * ec);
+#pragma unroll
+        for (int r = 0; r < 2; ++r) {
+          double2 xv[5], tv[5], uv[5];
+#pragma unroll
+          for (int j = 0; j < 5; ++j) {
+            const int c = l16 + 16 * (5 * r + j);
+            xv[j] = tile[c + c / 10];
+            if (RK) {
+              uv[j] = pu[c];                                                   // L1 hits: prefetched a phase ago
+              tv[j] = rk.a != 0.0 ? pt[c] : make_double2(0.0, 0.0);
+            }
+          }
+#pragma unroll
+          for (int j = 0; j < 5; ++j) {
+            const int c = l16 + 16 * (5 * r + j);
+            if (RK) {
+              const double t0 = fma(rk.a, tv[j].x, xv[j].x), t1 = fma(rk.a, tv[j].y, xv[j].y);
+              if (valid_c) {
+                __stcs(pt + c, make_double2(t0, t1));
+                __stcs(po + c, make_double2(fma(rk.b, t0, uv[j].x), fma(rk.b, t1, uv[j].y)));
+              }
+            } else if (valid_c) {
+              __stcs(po + c, xv[j]);
+            }
+          }
+        }
+      }
       __syncwarp();   // traces consumed, running sums visible
       if (dir == 0) issue_traces(D0{}, e_next, cn.x, cn.y);
       else if (dir == 1) issue_traces(D1{}, e_next, cn.x, cn.y);
@@ -419,10 +503,10 @@ k_line6(const __grid_constant__ Dev d, const __grid_constant__ LineOps ops, doub
 // batches of 2 and 5.3 ms with batches of 4 (local-memory spills of loop state, each reload an L2 round trip). The
 // kernel's time follows the SUM of the issue costs of its instructions, not the occupancy: 1 warp per scheduler already
 // reaches 70 % of the throughput of 2, and 3 add nothing (profiles/r1_line6_notes.md).
-template <int VFLUX, int SFLUX, bool SFV, int CTAS, int WARPS, int NP>
+template <int VFLUX, int SFLUX, bool SFV, int CTAS, int WARPS, int NP, bool RK = false, bool TOUT = false>
 static int line6_launch_t(const Dev& d, const LineOps& ops, double* du, const double* u, double t, const int* elems,
-                          int64_t count, cudaStream_t stream, int sm_count) {
-  auto kern = k_line6<VFLUX, SFLUX, SFV, WARPS, CTAS, NP>;
+                          int64_t count, cudaStream_t stream, int sm_count, const RkArgs& rk = RkArgs{nullptr, 0, 0, 0}) {
+  auto kern = k_line6<VFLUX, SFLUX, SFV, WARPS, CTAS, NP, RK, TOUT>;
   static bool configured = false;
   if (!configured) {
     if (cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)l6_smem(WARPS)) != cudaSuccess)
@@ -434,7 +518,7 @@ static int line6_launch_t(const Dev& d, const LineOps& ops, double* du, const do
   const int64_t npairs = (count + 1) / 2;
   const int64_t want = (npairs + WARPS - 1) / WARPS;
   const unsigned blocks = (unsigned)std::min<int64_t>(want, (int64_t)sm_count * CTAS);
-  kern<<<blocks, 32 * WARPS, l6_smem(WARPS), stream>>>(d, ops, du, u, t, elems, count);
+  kern<<<blocks, 32 * WARPS, l6_smem(WARPS), stream>>>(d, ops, du, u, t, elems, count, rk);
   return cudaGetLastError() == cudaSuccess ? 0 : TRIXIB200_ECUDA;
 }
 
@@ -446,10 +530,25 @@ static int line6_launch(const trixib200_config& c, const Dev& d, const LineOps& 
     // TRIXIB200_LINE_SHAPE=3: 3 CTAs x 4 warps per SM at 168 registers, batches of 2 pairs (A/B measurements)
     static const bool three = getenv("TRIXIB200_LINE_SHAPE") && atoi(getenv("TRIXIB200_LINE_SHAPE")) == 3;
     if (three && !sfv) return line6_launch_t<R, R, false, 3, 4, 2>(d, ops, du, u, t, elems, count, s, sm_count);
-    return sfv ? line6_launch_t<R, R, true, 2, 4, 8>(d, ops, du, u, t, elems, count, s, sm_count)
-               : line6_launch_t<R, R, false, 2, 4, 8>(d, ops, du, u, t, elems, count, s, sm_count);
+    // TRIXIB200_LINE_SHAPE=8: du stored directly from the x-line owners (160-byte runs per lane) instead of through
+    // the shared tile (A/B measurements: 4.71 vs 4.66 ms at level 7)
+    static const bool direct = getenv("TRIXIB200_LINE_SHAPE") && atoi(getenv("TRIXIB200_LINE_SHAPE")) == 8;
+    if (direct && !sfv) return line6_launch_t<R, R, false, 2, 4, 8>(d, ops, du, u, t, elems, count, s, sm_count);
+    return sfv ? line6_launch_t<R, R, true, 2, 4, 8, false, true>(d, ops, du, u, t, elems, count, s, sm_count)
+               : line6_launch_t<R, R, false, 2, 4, 8, false, true>(d, ops, du, u, t, elems, count, s, sm_count);
   }
-  return line6_launch_t<-1, -1, true, 2, 4, 2>(d, ops, du, u, t, elems, count, s, sm_count);
+  return line6_launch_t<-1, -1, true, 2, 4, 2, false, true>(d, ops, du, u, t, elems, count, s, sm_count);
+}
+
+// rhs! fused with the 2N Runge-Kutta stage update: u_out = u_in + b * (tmp = a * tmp + dt * rhs(u_in, t))
+static int line6_launch_rk(const trixib200_config& c, const Dev& d, const LineOps& ops, double* u_out, const double* u_in,
+                           double t, const int* elems, int64_t count, cudaStream_t s, int sm_count, const RkArgs& rk) {
+  constexpr int R = TRIXIB200_FLUX_RANOCHA;
+  const bool sfv = d.B > 0 || d.M > 0;
+  if (c.volume_flux == R && c.surface_flux == R)
+    return sfv ? line6_launch_t<R, R, true, 2, 4, 8, true>(d, ops, u_out, u_in, t, elems, count, s, sm_count, rk)
+               : line6_launch_t<R, R, false, 2, 4, 8, true>(d, ops, u_out, u_in, t, elems, count, s, sm_count, rk);
+  return line6_launch_t<-1, -1, true, 2, 4, 2, true>(d, ops, u_out, u_in, t, elems, count, s, sm_count, rk);
 }
 
 }  // namespace tb

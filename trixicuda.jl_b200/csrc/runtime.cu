@@ -249,6 +249,7 @@ struct trixib200_handle {
   int sm_count = 148;
   // rhs_host: library-owned device mirrors of the caller's host vectors, and the chunk pipeline
   double* host_u = nullptr; double* host_du = nullptr;
+  double* du_scratch = nullptr;            // rk2n_stage on kernel families without the fused epilogue (lazy)
   std::vector<int> face_nbr_host;          // kept for the chunk dependency analysis
   std::vector<double> chunk_key_src;       // last-dimension coordinate of every element (upload ordering)
   struct HostPipe {
@@ -694,13 +695,30 @@ static int rhs_staged(trixib200_handle* h, double* du, const double* u, double t
 }
 
 // one launch of the best fused kernel over a list (or, with elems == nullptr, the first `count`) of elements
-static int fused_launch_any(trixib200_handle* h, double* du, const double* u, double t, const int* elems, int64_t count) {
-  if (count <= 0) return 0;
-  Dev& d = h->d;
-  const bool w3 = h->warp3d && ((((uintptr_t)u) | ((uintptr_t)du)) & 15) == 0;
-  const bool l3 = w3 && h->line3d;
+static bool line_gen5() {
   // TRIXIB200_LINE_KERNEL=5 selects the previous generation of the line-owner kernel (A/B measurements)
   static const bool gen5 = getenv("TRIXIB200_LINE_KERNEL") && atoi(getenv("TRIXIB200_LINE_KERNEL")) == 5;
+  return gen5;
+}
+// can rhs! + 2N Runge-Kutta stage run as ONE launch (k_line6<..., RK = true>) on these vectors?
+static bool rk_fusable(const trixib200_handle* h, const double* u_out, const double* u_in, const double* tmp) {
+  return h->fused && h->line3d && !line_gen5() &&
+         ((((uintptr_t)u_out) | ((uintptr_t)u_in) | ((uintptr_t)tmp)) & 15) == 0;
+}
+
+static int fused_launch_any(trixib200_handle* h, double* du, const double* u, double t, const int* elems, int64_t count,
+                            const RkArgs* rk = nullptr) {
+  if (count <= 0) return 0;
+  Dev& d = h->d;
+  if (rk) {   // caller checked rk_fusable(): du is u_out here
+    if (int rc = line6_launch_rk(h->cfg, d, h->line_ops, du, u, t, elems, count, h->stream, h->sm_count, *rk))
+      return fail(rc, "fused RK launch failed");
+    h->launches++;
+    return 0;
+  }
+  const bool w3 = h->warp3d && ((((uintptr_t)u) | ((uintptr_t)du)) & 15) == 0;
+  const bool l3 = w3 && h->line3d;
+  const bool gen5 = line_gen5();
   int rc = (l3 && !gen5) ? line6_launch(h->cfg, d, h->line_ops, du, u, t, elems, count, h->stream, h->sm_count)
          : l3 ? line3d_launch(h->cfg, d, h->line_ops, du, u, t, elems, count, h->stream, h->sm_count)
          : w3 ? warp3d_launch(h->cfg, d, du, u, t, elems, count, h->stream, h->sm_count)
@@ -710,7 +728,7 @@ static int fused_launch_any(trixib200_handle* h, double* du, const double* u, do
   return 0;
 }
 
-static int rhs_fused(trixib200_handle* h, double* du, const double* u, double t) {
+static int rhs_fused(trixib200_handle* h, double* du, const double* u, double t, const RkArgs* rk = nullptr) {
   Dev& d = h->d;
   if (int rc = halo_begin(h, u)) return rc;
   if (d.volume_integral == TRIXIB200_VI_SHOCK_CAPTURING_HG) st_indicator(h, u);
@@ -719,7 +737,7 @@ static int rhs_fused(trixib200_handle* h, double* du, const double* u, double t)
   if (d.M > 0) { st_prolong_mortars(h, u); st_mortar_flux(h); }
   bool multi = h->cfg.nranks > 1 && d.nhalo_send > 0;
   // (the line-owner / warp-per-element kernels need 16-byte aligned vectors; fused_launch_any checks)
-  auto launch = [&](const int* elems, int64_t count) -> int { return fused_launch_any(h, du, u, t, elems, count); };
+  auto launch = [&](const int* elems, int64_t count) -> int { return fused_launch_any(h, du, u, t, elems, count, rk); };
   if (!multi) {
     if (int rc = launch(nullptr, d.E)) return rc;
   } else {
@@ -1012,6 +1030,64 @@ extern "C" int trixib200_rk2n_update(trixib200_handle* h, double* u, double* tmp
     h->launches++;
   }
   CUDA_TRY(cudaGetLastError());
+  return 0;
+}
+
+// out-of-place 2N stage for the kernel families without the fused epilogue
+__global__ void k_rk2n_stage_oop(double* __restrict__ u_out, const double* __restrict__ u_in, double* __restrict__ tmp,
+                                 const double* __restrict__ du, double a, double b, double dt, int64_t n) {
+  int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+  for (; i < n; i += stride) {
+    const double tn = a != 0.0 ? fma(a, tmp[i], dt * du[i]) : dt * du[i];
+    tmp[i] = tn;
+    u_out[i] = fma(b, tn, u_in[i]);
+  }
+}
+
+extern "C" int trixib200_rk2n_stage(trixib200_handle* h, double* u_out, const double* u_in, double* tmp, double t,
+                                    double a, double b, double dt) {
+  if (!h || !u_out || !u_in || !tmp) return fail(TRIXIB200_EINVAL, "null argument");
+  if (u_out == u_in) return fail(TRIXIB200_EINVAL, "rk2n_stage: u_out must not alias u_in (neighbours read u_in)");
+  CUDA_TRY(cudaSetDevice(h->cfg.device));
+  if (rk_fusable(h, u_out, u_in, tmp)) {
+    const RkArgs rk{tmp, a, b, dt};
+    if (int rc = rhs_fused(h, u_out, u_in, t, &rk)) return rc;
+    CUDA_TRY(cudaGetLastError());
+    return 0;
+  }
+  const int64_t n = h->d.E * h->d.nn * h->d.nv;
+  if (!h->du_scratch)
+    if (int rc = dalloc(h, (size_t)n, &h->du_scratch, false)) return rc;
+  if (int rc = trixib200_rhs(h, h->du_scratch, u_in, t)) return rc;
+  if (n > 0) {
+    const int64_t blocks = std::min<int64_t>((n + 255) / 256, (int64_t)h->sm_count * 16);
+    k_rk2n_stage_oop<<<(unsigned)blocks, 256, 0, h->stream>>>(u_out, u_in, tmp, h->du_scratch, a, b, dt, n);
+    h->launches++;
+  }
+  CUDA_TRY(cudaGetLastError());
+  return 0;
+}
+
+// CarpenterKennedy2N54 coefficients (Trixi / OrdinaryDiffEq `CarpenterKennedy2N54`)
+static const double CK_A[5] = {0.0, -567301805773.0 / 1357537059087.0, -2404267990393.0 / 2016746695238.0,
+                               -3550918686646.0 / 2091501179385.0, -1275806237668.0 / 842570457699.0};
+static const double CK_B[5] = {1432997174477.0 / 9575080441755.0, 5161836677717.0 / 13612068292357.0,
+                               1720146321549.0 / 2090206949498.0, 3134564353537.0 / 4481467310338.0,
+                               2277821191437.0 / 14882151754819.0};
+static const double CK_C[5] = {0.0, 1432997174477.0 / 9575080441755.0, 2526269341429.0 / 6820363962896.0,
+                               2006345519317.0 / 3224310063776.0, 2802321613138.0 / 2924317926251.0};
+
+extern "C" int trixib200_rk2n_step_ck54(trixib200_handle* h, double* u, double* u_alt, double* tmp, double t, double dt,
+                                        int* result_in_alt) {
+  if (!h || !u || !u_alt || !tmp) return fail(TRIXIB200_EINVAL, "null argument");
+  double* cur = u;
+  double* nxt = u_alt;
+  for (int s = 0; s < 5; ++s) {
+    if (int rc = trixib200_rk2n_stage(h, nxt, cur, tmp, t + CK_C[s] * dt, CK_A[s], CK_B[s], dt)) return rc;
+    std::swap(cur, nxt);
+  }
+  if (result_in_alt) *result_in_alt = (cur == u_alt) ? 1 : 0;
   return 0;
 }
 

@@ -87,12 +87,16 @@ def calc_error_norms(u_ode, t, analyzer, semi):
     return l2, linf
 
 
-def solve(ode, alg=None, dt=1.0, callback=None, maxiters=10 ** 9, **_ignored):
-    """Low-storage RK loop: `tmp = A_s tmp + dt f(u, t + c_s dt); u += B_s tmp`."""
+def solve(ode, alg=None, dt=1.0, callback=None, maxiters=10 ** 9, fused_stages=False, **_ignored):
+    """Low-storage RK loop: `tmp = A_s tmp + dt f(u, t + c_s dt); u += B_s tmp`.
+
+    fused_stages=True runs every stage as ONE library call (`trixib200_rk2n_stage`: rhs! and the 2N update in the
+    same kernel on the line-owner path), ping-ponging between two state vectors."""
     semi = ode.p
     u = ode.u0.clone()
     du = semi.new_vector()
     tmp = semi.new_vector().zero_()
+    u_alt = semi.new_vector() if fused_stages else None
     t, t_end = float(ode.tspan[0]), float(ode.tspan[1])
     cb = callback if isinstance(callback, CallbackSet) else CallbackSet(*( [callback] if callback else [] ))
     step_cb, ana_cb = cb.find(StepsizeCallback), cb.find(AnalysisCallback)
@@ -104,9 +108,14 @@ def solve(ode, alg=None, dt=1.0, callback=None, maxiters=10 ** 9, **_ignored):
             dt = step_cb.cfl * semi.max_dt(u, t)
         if t + dt > t_end or abs(t + dt - t_end) < 100 * 2.2e-16 * max(1.0, abs(t_end)):
             dt = t_end - t
-        for s in range(5):
-            ode.f(du, u, semi, t + _C[s] * dt)
-            semi.rk2n_update(u, tmp, du, _A[s], _B[s], dt)
+        if fused_stages:
+            res = semi.rk2n_step_ck54(u, u_alt, tmp, t, dt)
+            if res is u_alt:
+                u, u_alt = u_alt, u
+        else:
+            for s in range(5):
+                ode.f(du, u, semi, t + _C[s] * dt)
+                semi.rk2n_update(u, tmp, du, _A[s], _B[s], dt)
         t += dt
         nsteps += 1
         if ana_cb is not None and ana_cb.interval > 0 and nsteps % ana_cb.interval == 0:

@@ -250,6 +250,21 @@ class SemidiscretizationHyperbolicGPU:
         self._sync_stream()
         _lib.check(self._L.trixib200_rk2n_update(self._h, u.data_ptr(), tmp.data_ptr(), du.data_ptr(), a, b, dt))
 
+    def rk2n_stage(self, u_out, u_in, tmp, t, a, b, dt):
+        """rhs! fused with one 2N Runge-Kutta stage: tmp = a tmp + dt rhs(u_in, t); u_out = u_in + b tmp
+        (trixib200_rk2n_stage; one launch on the line-owner kernel path, du never materialised)."""
+        self._sync_stream()
+        _lib.check(self._L.trixib200_rk2n_stage(self._h, u_out.data_ptr(), u_in.data_ptr(), tmp.data_ptr(), float(t),
+                                                float(a), float(b), float(dt)))
+
+    def rk2n_step_ck54(self, u, u_alt, tmp, t, dt):
+        """One CarpenterKennedy2N54 step; returns the vector that holds the result (u_alt after five stages)."""
+        self._sync_stream()
+        flag = C.c_int(0)
+        _lib.check(self._L.trixib200_rk2n_step_ck54(self._h, u.data_ptr(), u_alt.data_ptr(), tmp.data_ptr(), float(t),
+                                                    float(dt), C.byref(flag)))
+        return u_alt if flag.value else u
+
     def launch_count(self):
         return int(self._L.trixib200_launch_count(self._h))
 
