@@ -215,4 +215,32 @@ function Trixi.max_dt(u::CuArray{Float64}, t, mesh::TreeMesh, constant_speed, eq
     return out[]
 end
 
+# ------------------------------------------------------------------------------------------------ fused RK stages
+# Optional fast path (SURVEY.md section 8(f) row 1): OrdinaryDiffEq's `perform_step!` for `CarpenterKennedy2N54` is
+# `rhs_gpu!` followed by two broadcasts per stage; `trixib200_rk2n_stage` does rhs! and the 2N update in one kernel
+# and never writes du. `step_ck2n54!` advances (u, t) by dt with five fused stages, ping-ponging between u and u_alt,
+# and returns the vector that holds the new state. A `DiscreteCallback`-free driver can call it in a plain loop with
+# Trixi's StepsizeCallback logic (`dt = cfl * max_dt(u, ...)`).
+function rk2n_stage!(u_out::CuVector{Float64}, u_in::CuVector{Float64}, tmp::CuVector{Float64},
+                     semi::SemidiscretizationHyperbolicGPU, t, a, b, dt)
+    check(ccall((:trixib200_set_stream, LIB), Cint, (Ptr{Cvoid}, Int64), semi.cache_gpu,
+                reinterpret(Int64, stream().handle)))
+    check(ccall((:trixib200_rk2n_stage, LIB), Cint,
+                (Ptr{Cvoid}, Ptr{Float64}, Ptr{Float64}, Ptr{Float64}, Float64, Float64, Float64, Float64),
+                semi.cache_gpu, reinterpret(Ptr{Float64}, pointer(u_out)), reinterpret(Ptr{Float64}, pointer(u_in)),
+                reinterpret(Ptr{Float64}, pointer(tmp)), t, a, b, dt))
+    return nothing
+end
+function step_ck2n54!(u::CuVector{Float64}, u_alt::CuVector{Float64}, tmp::CuVector{Float64},
+                      semi::SemidiscretizationHyperbolicGPU, t, dt)
+    in_alt = Ref{Cint}(0)
+    check(ccall((:trixib200_set_stream, LIB), Cint, (Ptr{Cvoid}, Int64), semi.cache_gpu,
+                reinterpret(Int64, stream().handle)))
+    check(ccall((:trixib200_rk2n_step_ck54, LIB), Cint,
+                (Ptr{Cvoid}, Ptr{Float64}, Ptr{Float64}, Ptr{Float64}, Float64, Float64, Ref{Cint}), semi.cache_gpu,
+                reinterpret(Ptr{Float64}, pointer(u)), reinterpret(Ptr{Float64}, pointer(u_alt)),
+                reinterpret(Ptr{Float64}, pointer(tmp)), t, dt, in_alt))
+    return in_alt[] == 1 ? u_alt : u
+end
+
 end # module
