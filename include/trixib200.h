@@ -188,6 +188,19 @@ int trixib200_rk2n_stage(trixib200_handle* h, double* u_out, const double* u_in,
 int trixib200_rk2n_step_ck54(trixib200_handle* h, double* u, double* u_alt, double* tmp, double t, double dt,
                              int* result_in_alt);
 
+/* Device-side AnalysisCallback pieces. replaces: calc_error_norms(cons2cons, u, t,
+ * analyzer, mesh, equations, initial_condition, dg, cache, cache_analysis) and integrate(cons2cons, u, ...)
+ * (reference src/callbacks_step/analysis_dg_3d.jl:45-89 and :1-42, analysis_dg_2d.jl, analysis_dg_1d.jl), which copy u
+ * and node_coordinates to the host and loop serially. `vandermonde` is the SolutionAnalyzer's interpolation matrix,
+ * ROW-major [n_analysis][nnodes], `weights` its quadrature weights [n_analysis] (host pointers); the initial condition
+ * is the handle's enumerated one evaluated at time t; total_volume = total_volume(mesh). Outputs are host arrays of
+ * nvars doubles: l2 = sqrt(sum diff^2 w J / total_volume), linf = max |diff| -- reduced over all ranks. Synchronous. */
+int trixib200_calc_error_norms(trixib200_handle* h, const double* u, double t, int32_t n_analysis,
+                               const double* vandermonde, const double* weights, double total_volume,
+                               double* l2_out, double* linf_out);
+/* integral of the conserved variables over the domain, divided by total_volume if normalize != 0 */
+int trixib200_integrate(trixib200_handle* h, const double* u, int32_t normalize, double total_volume, double* out);
+
 /* timing helpers: run rhs `reps` times back to back and return the elapsed device time in milliseconds,
  * measured with CUDA events on the handle's stream */
 int trixib200_time_rhs(trixib200_handle* h, double* du, const double* u, double t, int reps, float* ms_out);

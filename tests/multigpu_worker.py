@@ -44,6 +44,22 @@ def main():
             assert err <= 1e-12, (name, staged, rank, err)
             dt = semi.max_dt(u_d, 0.0)
             assert abs(dt - dt_ref) <= 1e-13 * dt_ref, (name, dt, dt_ref)
+            if not staged:
+                # device-side analysis reductions are reduced over the ranks (trixib200_calc_error_norms / integrate)
+                import trixib200 as T
+                l2, linf = semi.calc_error_norms(u_d, 0.4, T.SolutionAnalyzer(semi.solver.basis))
+                l2_ref, linf_ref = o.error_norms(u, 0.4)
+                assert np.abs(l2 - l2_ref).max() <= 1e-13 * max(1.0, np.abs(l2_ref).max()), (name, l2, l2_ref)
+                assert np.abs(linf - linf_ref).max() <= 1e-12 * max(1.0, np.abs(linf_ref).max()), (name, linf, linf_ref)
+                integ, integ_ref = semi.integrate(u_d, normalize=False), o.integrate(u)
+                assert np.abs(integ - integ_ref).max() <= 1e-13 * max(1.0, np.abs(integ_ref).max()), (name, integ)
+                # fused Runge-Kutta stage on the partition: same two element lists, halo exchange inside
+                tmp = semi.new_vector().zero_()
+                u_out = semi.new_vector().fill_(float("nan"))
+                semi.rk2n_stage(u_out, u_d, tmp, 0.1, 0.0, 0.25, 1e-3)
+                torch.cuda.synchronize()
+                ref_out = semi.local_slice(u + 0.25 * 1e-3 * du_ref)
+                assert np.abs(u_out.cpu().numpy() - ref_out).max() <= 1e-12 * 1e-3 * np.abs(du_ref).max() + 4e-16 * np.abs(ref_out).max(), (name, "rk2n_stage")
             du_h = np.full_like(lo, np.nan)
             semi.rhs_host(du_h, np.ascontiguousarray(lo), 0.1)
             assert np.array_equal(du_h, got), (name, staged, "rhs_host")

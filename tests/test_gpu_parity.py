@@ -228,6 +228,46 @@ def test_full_run_with_fused_rk_stages(name, tend, cfl):
     assert rel_max_err(sol.u[-1].cpu().numpy(), u_ref) <= 1e-10
 
 
+@pytest.mark.parametrize("name", ["c1_advection_1d", "c2_euler_ec_2d", "c5_euler_ec_3d", "c4_mhd_alfven_mortar_3d",
+                                  "euler_source_terms_3d", "advection_mortar_3d_p4", "euler_ec_2d_p5"])
+def test_device_error_norms_and_integrals(name):
+    """trixib200_calc_error_norms / trixib200_integrate (device reductions) against the oracle's restatement of Trixi's
+    calc_error_norms / integrate (reference src/callbacks_step/analysis_dg_3d.jl:1-89) on a state that is NOT the
+    initial condition (so the errors are O(1) and every variable contributes)."""
+    import trixib200 as T
+    c = CASES[name]
+    o, semi = make_oracle(c), make_semi(c)
+    rng = np.random.default_rng(11)
+    u = o.compute_coefficients(0.0)
+    u = u * (1.0 + 0.05 * rng.uniform(-1, 1, size=u.size))
+    t = 0.3
+    l2_ref, linf_ref = o.error_norms(u, t)
+    ana = T.AnalysisCallback(semi, on_device=True)
+    l2, linf = ana(_to_dev(semi, u), t)
+    assert np.abs(l2 - l2_ref).max() <= 1e-13 * max(1.0, np.abs(l2_ref).max())
+    assert np.abs(linf - linf_ref).max() <= 1e-13 * max(1.0, np.abs(linf_ref).max())
+    # exactly the initial condition: errors of the polynomial interpolation only, same numbers as on the CPU
+    u0 = o.compute_coefficients(t)
+    l2_ref0, linf_ref0 = o.error_norms(u0, t)
+    l20, linf0 = semi.calc_error_norms(_to_dev(semi, u0), t, ana.analyzer)
+    assert np.abs(l20 - l2_ref0).max() <= 1e-13 and np.abs(linf0 - linf_ref0).max() <= 1e-12
+    integ_ref = o.integrate(u)
+    integ = semi.integrate(_to_dev(semi, u), normalize=False)
+    assert np.abs(integ - integ_ref).max() <= 1e-13 * max(1.0, np.abs(integ_ref).max())
+
+
+def test_full_run_device_analysis():
+    """examples/advection_basic_1d.jl end to end with the analysis on the device: Trixi's published norms."""
+    import trixib200 as T
+    semi = make_semi(CASES["c1_advection_1d"])
+    ode = T.semidiscretizeGPU(semi, (0.0, 1.0))
+    ana = T.AnalysisCallback(semi, interval=100, on_device=True)
+    T.solve(ode, T.CarpenterKennedy2N54(williamson_condition=False), dt=1.0,
+            callback=T.CallbackSet(ana, T.StepsizeCallback(cfl=1.6)))
+    _, l2, linf = ana.history[-1]
+    assert abs(l2[0] - 6.0388296447998465e-6) <= 1e-10 and abs(linf[0] - 3.217887726258972e-5) <= 1e-10
+
+
 def test_large_mesh_properties():
     """Size-independent properties at a size the oracle would not finish in seconds (3D Euler EC, level 5,
     2.1 M DOF): free-stream preservation, discrete conservation and entropy conservation of the EC scheme."""

@@ -11,7 +11,7 @@ import numpy as np
 _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_HERE, "libtrixib200.so")
 CSRC = os.path.join(_HERE, "csrc")
-SOURCES = ["runtime.cu", "kernels_staged.cuh", "kernels_fused.cuh", "kernels_warp3d.cuh", "kernels_line3d.cuh", "kernels_line6.cuh", "equations.cuh",
+SOURCES = ["runtime.cu", "kernels_analysis.cuh", "kernels_staged.cuh", "kernels_fused.cuh", "kernels_warp3d.cuh", "kernels_line3d.cuh", "kernels_line6.cuh", "equations.cuh",
            "device.cuh"]
 NVCC_FLAGS = ["-O3", "-std=c++17", "-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo",
               "-shared", "-Xcompiler", "-fPIC"]
@@ -62,7 +62,7 @@ EXPORTS = [
     "trixib200_last_error", "trixib200_version", "trixib200_create", "trixib200_destroy", "trixib200_size",
     "trixib200_rhs", "trixib200_max_dt", "trixib200_stage", "trixib200_cache_len", "trixib200_cache_get",
     "trixib200_alloc", "trixib200_free", "trixib200_upload", "trixib200_download", "trixib200_sync",
-    "trixib200_stream", "trixib200_fill_initial_condition", "trixib200_rk2n_update", "trixib200_rk2n_stage", "trixib200_rk2n_step_ck54",
+    "trixib200_stream", "trixib200_fill_initial_condition", "trixib200_rk2n_update", "trixib200_rk2n_stage", "trixib200_rk2n_step_ck54", "trixib200_calc_error_norms", "trixib200_integrate",
     "trixib200_time_rhs",
     "trixib200_launch_count", "trixib200_comm_unique_id", "trixib200_comm_init", "trixib200_set_stream",
     "trixib200_rhs_host", "trixib200_host_register", "trixib200_host_unregister",
@@ -135,6 +135,9 @@ def lib():
                                        C.c_double, C.c_double]
     L.trixib200_rk2n_step_ck54.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_double, C.c_double,
                                            C.POINTER(C.c_int)]
+    L.trixib200_calc_error_norms.argtypes = [C.c_void_p, C.c_void_p, C.c_double, C.c_int32, C.c_void_p, C.c_void_p,
+                                             C.c_double, C.c_void_p, C.c_void_p]
+    L.trixib200_integrate.argtypes = [C.c_void_p, C.c_void_p, C.c_int32, C.c_double, C.c_void_p]
     L.trixib200_time_rhs.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_double, C.c_int,
                                      C.POINTER(C.c_float)]
     L.trixib200_launch_count.restype = C.c_int64

@@ -19,6 +19,7 @@
 #include "kernels_warp3d.cuh"
 #include "kernels_line3d.cuh"
 #include "kernels_line6.cuh"
+#include "kernels_analysis.cuh"
 
 using namespace tb;
 
@@ -60,7 +61,7 @@ struct Nccl {
   }
 };
 static Nccl g_nccl;
-constexpr int NCCL_FLOAT64 = 8, NCCL_MAX = 2;
+constexpr int NCCL_FLOAT64 = 8, NCCL_SUM = 0, NCCL_MAX = 2;
 
 
 // ---------------------------------------------------------------------------------------------- partition plan
@@ -249,6 +250,7 @@ struct trixib200_handle {
   int sm_count = 148;
   // rhs_host: library-owned device mirrors of the caller's host vectors, and the chunk pipeline
   double* host_u = nullptr; double* host_du = nullptr;
+  double* an_buf = nullptr;                // analysis kernels: operators + per-CTA partials (lazy)
   double* du_scratch = nullptr;            // rk2n_stage on kernel families without the fused epilogue (lazy)
   std::vector<int> face_nbr_host;          // kept for the chunk dependency analysis
   std::vector<double> chunk_key_src;       // last-dimension coordinate of every element (upload ordering)
@@ -1133,6 +1135,89 @@ extern "C" int trixib200_rk2n_step_ck54(trixib200_handle* h, double* u, double* 
     std::swap(cur, nxt);
   }
   if (result_in_alt) *result_in_alt = (cur == u_alt) ? 1 : 0;
+  return 0;
+}
+
+// ---------------------------------------------------------------------------------------------- analysis
+constexpr int AN_GRID = 1024;   // CTAs (= partials per variable) of the analysis kernels
+static int analysis_buffers(trixib200_handle* h) {
+  if (h->an_buf) return 0;
+  return dalloc(h, (size_t)AN_GRID * 2 * AN_MAXV + 16 * MAXN + 64, &h->an_buf, false);
+}
+// sum / max of the local values over the ranks (in place, host vectors of n <= AN_MAXV doubles)
+static int analysis_allreduce(trixib200_handle* h, double* v, int n, bool max) {
+  if (h->cfg.nranks == 1) return 0;
+  if (!h->comm) return fail(TRIXIB200_ECOMM, "nranks > 1 but trixib200_comm_init was not called");
+  CUDA_TRY(cudaMemcpyAsync(h->an_buf, v, n * sizeof(double), cudaMemcpyHostToDevice, h->stream));
+  if (g_nccl.AllReduce(h->an_buf, h->an_buf, n, NCCL_FLOAT64, max ? NCCL_MAX : NCCL_SUM, h->comm, h->stream) != 0)
+    return fail(TRIXIB200_ECOMM, "ncclAllReduce failed");
+  CUDA_TRY(cudaMemcpyAsync(v, h->an_buf, n * sizeof(double), cudaMemcpyDeviceToHost, h->stream));
+  CUDA_TRY(cudaStreamSynchronize(h->stream));
+  return 0;
+}
+
+extern "C" int trixib200_calc_error_norms(trixib200_handle* h, const double* u, double t, int32_t n_analysis,
+                                          const double* vandermonde, const double* weights, double total_volume,
+                                          double* l2_out, double* linf_out) {
+  if (!h || !u || !vandermonde || !weights || !l2_out || !linf_out) return fail(TRIXIB200_EINVAL, "null argument");
+  CUDA_TRY(cudaSetDevice(h->cfg.device));
+  Dev& d = h->d;
+  const int NA = n_analysis, nv = d.nv;
+  if (NA < 1 || NA > 2 * MAXN) return fail(TRIXIB200_EINVAL, "calc_error_norms: 1 <= n_analysis <= 16");
+  if (!d.node_coords && !d.centers) return fail(TRIXIB200_EINVAL, "calc_error_norms needs node_coordinates or cell_centers");
+  if (!(total_volume > 0)) return fail(TRIXIB200_EINVAL, "calc_error_norms: total_volume must be positive");
+  const size_t smem = analysis_smem_doubles(d.ndim, d.N, NA, nv) * sizeof(double);
+  if (smem > 200 * 1024) return fail(TRIXIB200_EUNSUPPORTED, "calc_error_norms: analysis tile exceeds shared memory");
+  if (int rc = analysis_buffers(h)) return rc;
+  double* dV = h->an_buf + (size_t)AN_GRID * 2 * AN_MAXV;
+  double* dw = dV + 16 * MAXN;
+  CUDA_TRY(cudaMemcpyAsync(dV, vandermonde, (size_t)NA * d.N * sizeof(double), cudaMemcpyHostToDevice, h->stream));
+  CUDA_TRY(cudaMemcpyAsync(dw, weights, (size_t)NA * sizeof(double), cudaMemcpyHostToDevice, h->stream));
+  const int grid = (int)std::min<int64_t>(std::max<int64_t>(d.E, 1), AN_GRID);
+  TB_DISPATCH_EQ(h, {
+    auto kern = k_error_norms<Eq>;
+    if (cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess)
+      return fail(TRIXIB200_ECUDA, "calc_error_norms: shared memory opt-in failed");
+    kern<<<grid, AN_THREADS, smem, h->stream>>>(d, u, t, NA, dV, dw, h->an_buf);
+    h->launches++;
+  });
+  CUDA_TRY(cudaGetLastError());
+  std::vector<double> part((size_t)grid * 2 * nv);
+  CUDA_TRY(cudaMemcpyAsync(part.data(), h->an_buf, part.size() * sizeof(double), cudaMemcpyDeviceToHost, h->stream));
+  CUDA_TRY(cudaStreamSynchronize(h->stream));
+  double l2[AN_MAXV], li[AN_MAXV];
+  for (int v = 0; v < nv; ++v) { l2[v] = 0; li[v] = 0; }
+  for (int b = 0; b < grid; ++b)
+    for (int v = 0; v < nv; ++v) {
+      l2[v] += part[(2 * (size_t)b + 0) * nv + v];
+      li[v] = std::max(li[v], part[(2 * (size_t)b + 1) * nv + v]);
+    }
+  if (int rc = analysis_allreduce(h, l2, nv, false)) return rc;
+  if (int rc = analysis_allreduce(h, li, nv, true)) return rc;
+  for (int v = 0; v < nv; ++v) { l2_out[v] = std::sqrt(l2[v] / total_volume); linf_out[v] = li[v]; }
+  return 0;
+}
+
+extern "C" int trixib200_integrate(trixib200_handle* h, const double* u, int32_t normalize, double total_volume,
+                                   double* out) {
+  if (!h || !u || !out) return fail(TRIXIB200_EINVAL, "null argument");
+  if (normalize && !(total_volume > 0)) return fail(TRIXIB200_EINVAL, "integrate: total_volume must be positive");
+  CUDA_TRY(cudaSetDevice(h->cfg.device));
+  Dev& d = h->d;
+  const int nv = d.nv;
+  if (int rc = analysis_buffers(h)) return rc;
+  const int grid = (int)std::min<int64_t>(std::max<int64_t>(d.E, 1), AN_GRID);
+  TB_DISPATCH_EQ(h, { k_integrate<Eq><<<grid, AN_THREADS, 0, h->stream>>>(d, u, h->an_buf); h->launches++; });
+  CUDA_TRY(cudaGetLastError());
+  std::vector<double> part((size_t)grid * nv);
+  CUDA_TRY(cudaMemcpyAsync(part.data(), h->an_buf, part.size() * sizeof(double), cudaMemcpyDeviceToHost, h->stream));
+  CUDA_TRY(cudaStreamSynchronize(h->stream));
+  double acc[AN_MAXV];
+  for (int v = 0; v < nv; ++v) acc[v] = 0;
+  for (int b = 0; b < grid; ++b)
+    for (int v = 0; v < nv; ++v) acc[v] += part[(size_t)b * nv + v];
+  if (int rc = analysis_allreduce(h, acc, nv, false)) return rc;
+  for (int v = 0; v < nv; ++v) out[v] = normalize ? acc[v] / total_volume : acc[v];
   return 0;
 }
 

@@ -265,6 +265,26 @@ class SemidiscretizationHyperbolicGPU:
                                                     float(dt), C.byref(flag)))
         return u_alt if flag.value else u
 
+    def calc_error_norms(self, u, t, analyzer):
+        """`calc_error_norms(cons2cons, u, t, analyzer, ...)` on the device (trixib200_calc_error_norms): L2 / Linf
+        errors against the enumerated initial condition at time t on the analyzer's nodes, reduced over all ranks."""
+        self._sync_stream()
+        V = np.ascontiguousarray(analyzer.vandermonde, dtype=np.float64)       # [n_analysis, nnodes] row-major
+        w = np.ascontiguousarray(analyzer.weights, dtype=np.float64)
+        l2, linf = np.empty(self.nvars), np.empty(self.nvars)
+        vol = float(self.mesh.length_level_0) ** self.mesh.ndim
+        _lib.check(self._L.trixib200_calc_error_norms(self._h, u.data_ptr(), float(t), int(V.shape[0]), _lib.fptr(V),
+                                                      _lib.fptr(w), vol, _lib.fptr(l2), _lib.fptr(linf)))
+        return l2, linf
+
+    def integrate(self, u, normalize=True):
+        """`integrate(cons2cons, u, ...)` on the device: domain integrals of the conserved variables."""
+        self._sync_stream()
+        out = np.empty(self.nvars)
+        vol = float(self.mesh.length_level_0) ** self.mesh.ndim
+        _lib.check(self._L.trixib200_integrate(self._h, u.data_ptr(), int(bool(normalize)), vol, _lib.fptr(out)))
+        return out
+
     def launch_count(self):
         return int(self._L.trixib200_launch_count(self._h))
 
