@@ -220,6 +220,35 @@ def run_ours(args):
     if not bool(torch.isfinite(du).all().item()):
         raise SystemExit("bench.py: non-finite du")
 
+    # ---- context: one CarpenterKennedy2N54 stage, rhs! + update kernel vs the fused trixib200_rk2n_stage
+    extras = {}
+    try:
+        u2, tmp = semi.new_vector(), semi.new_vector().zero_()
+        a, b, dt = -0.4178904745, 0.3792103129999, 1e-4
+
+        def timed(fn, reps=min(K, 10)):
+            for _ in range(2):
+                fn()
+            barrier()
+            f0, f1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            f0.record()
+            for _ in range(reps):
+                fn()
+            f1.record()
+            barrier()
+            return max_over_ranks(f0.elapsed_time(f1)) / reps
+
+        def unfused():
+            T.rhs_gpu_(du, u, semi, 0.0)
+            semi.rk2n_update(u2, tmp, du, a, b, dt)
+
+        extras = {"rk2n_stage_unfused_ms": timed(unfused),
+                  "rk2n_stage_fused_ms": timed(lambda: semi.rk2n_stage(u2, u, tmp, 0.0, a, b, dt)),
+                  "note": "one 2N Runge-Kutta stage at the same size: rhs! + update kernel vs trixib200_rk2n_stage"}
+        del u2, tmp
+    except Exception as ex:  # context only: never fail the bench line over it
+        extras = {"error": repr(ex)}
+
     # ---- end to end: host vectors in, host vectors out, every step
     e2e = None
     if not args.no_e2e:
@@ -273,7 +302,10 @@ def run_ours(args):
                 "algorithmic_bytes_per_dof": BYTES_PER_DOF,
                 "fp64": {"algorithmic_flop_per_dof": FLOP_PER_DOF,
                          "achieved_tflops": FLOP_PER_DOF * ndofs_local / (ms_step * 1e-3) / 1e12,
-                         "peak_tflops_measured_dfma": fp64_peak}}
+                         "peak_tflops_measured_dfma": fp64_peak,
+                         "frac": (FLOP_PER_DOF * ndofs_local / (ms_step * 1e-3) / 1e12 / fp64_peak) if fp64_peak else None,
+                         "note": "issue-bound: time = sum of the issue costs of ~1350 FP64 (2 cycles) and ~1300 other "
+                                 "instructions per element pair and scheduler (profiles/r1_line6_notes.md)"}}
     line = {"metric": "rhs! DOF-updates/s (1/PID) 3D Euler EC p=3", "value": value, "unit": "DOF-updates/s",
             "n_gpus": world, "steps": K, "warmup": W, "ms_per_step": ms_step, "higher_is_better": True,
             "scaling": "strong", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
@@ -284,7 +316,8 @@ def run_ours(args):
                        "partition": f"morton{world}", "l2_policy": "inputs larger than L2 "
                        f"(u+du = {2 * 40 * ndofs_local / 1e9:.2f} GB per rank vs 126 MB L2), no flush",
                        "setup_s": round(setup_s, 1)},
-            "roofline": roofline, "e2e": e2e, "gpu_launches": int(launches), "clocks": clocks.summary()}
+            "roofline": roofline, "e2e": e2e, "gpu_launches": int(launches), "clocks": clocks.summary(),
+            "extras": extras}
     if world == 1 and not args.no_cpu:
         v, cores, sample, ms, reps = cpu_sample(args.cpu_level)
         line["cpu_baseline"] = {"value": v, "unit": "DOF-updates/s", "cores": cores, "kind": "port",
