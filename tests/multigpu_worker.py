@@ -52,7 +52,8 @@ def main():
                 assert np.abs(l2 - l2_ref).max() <= 1e-13 * max(1.0, np.abs(l2_ref).max()), (name, l2, l2_ref)
                 assert np.abs(linf - linf_ref).max() <= 1e-12 * max(1.0, np.abs(linf_ref).max()), (name, linf, linf_ref)
                 integ, integ_ref = semi.integrate(u_d, normalize=False), o.integrate(u)
-                assert np.abs(integ - integ_ref).max() <= 1e-13 * max(1.0, np.abs(integ_ref).max()), (name, integ)
+                # (sums of ~1e5 terms in a different order on every rank count: round-off of the summation)
+                assert np.abs(integ - integ_ref).max() <= 2e-12 * max(1.0, np.abs(integ_ref).max()), (name, integ - integ_ref)
                 # fused Runge-Kutta stage on the partition: same two element lists, halo exchange inside
                 tmp = semi.new_vector().zero_()
                 u_out = semi.new_vector().fill_(float("nan"))

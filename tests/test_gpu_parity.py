@@ -253,7 +253,7 @@ def test_device_error_norms_and_integrals(name):
     assert np.abs(l20 - l2_ref0).max() <= 1e-13 and np.abs(linf0 - linf_ref0).max() <= 1e-12
     integ_ref = o.integrate(u)
     integ = semi.integrate(_to_dev(semi, u), normalize=False)
-    assert np.abs(integ - integ_ref).max() <= 1e-13 * max(1.0, np.abs(integ_ref).max())
+    assert np.abs(integ - integ_ref).max() <= 2e-12 * max(1.0, np.abs(integ_ref).max())   # summation order
 
 
 def test_full_run_device_analysis():
