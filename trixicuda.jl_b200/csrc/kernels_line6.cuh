@@ -118,7 +118,7 @@ k_line6(const __grid_constant__ Dev d, const __grid_constant__ LineOps ops, doub
   extern __shared__ __align__(16) double smem_l6[];
   // Per-lane constants live in two OPAQUE registers (a self-shuffle hides their origin): under register pressure ptxas
   // otherwise re-derives them from S2R SR_TID.X + an integer chain in every phase (short-scoreboard stalls at the top
-  // of each phase in profiles/r1_ncu_line6_a.txt); from the packed word they cost one or two ALU ops.
+  // of each phase in profiles/r1_ncu_line6_12warps_l6_hot.txt); from the packed word they cost one or two ALU ops.
   unsigned lp = threadIdx.x & 31;          // l16 | half << 4
   unsigned sb = (unsigned)__cvta_generic_to_shared(smem_l6) +
                 (unsigned)((2 * (threadIdx.x >> 5) + ((threadIdx.x >> 4) & 1)) * L6_EL * sizeof(double));
@@ -127,7 +127,6 @@ k_line6(const __grid_constant__ Dev d, const __grid_constant__ LineOps ops, doub
   sb = __shfl_sync(0xffffffffu, sb, threadIdx.x & 31);
   const int half = lp >> 4, l16 = lp & 15;
   const int la = l16 & 3, lb = l16 >> 2;
-  const int warp = 0;                      // (only used through wid below)
   double* ebase = reinterpret_cast<double*>(__cvta_shared_to_generic((size_t)sb));
   double* sq = ebase;                    // AoS landing zone of the element block, then the swizzled SoA q [5][64]
   double* sacc = ebase + L6_TILE;        // swizzled SoA running sums [5][64], handed from phase to phase
@@ -137,7 +136,7 @@ k_line6(const __grid_constant__ Dev d, const __grid_constant__ LineOps ops, doub
   const int vflux = (VFLUX >= 0) ? VFLUX : d.vol_flux;
   const int sflux = (SFLUX >= 0) ? SFLUX : d.surf_flux;
   const int npairs = (int)((count + 1) >> 1);          // element ids are int (face_nbr), so pair indices fit
-  const int wid = blockIdx.x * WARPS + (threadIdx.x >> 5) + warp, nw = gridDim.x * WARPS;
+  const int wid = blockIdx.x * WARPS + (threadIdx.x >> 5), nw = gridDim.x * WARPS;
 
   auto elem_of = [&](int pr, bool& valid) -> int {
     int s = 2 * pr + half;
