@@ -227,3 +227,46 @@ def test_coordinate_permutation_symmetry_3d():
     perm = np.array([key[tuple(np.round(c[[1, 0, 2]], 9))] for c in cen])
     du2m = du2[perm].transpose(0, 1, 3, 2, 4)[..., [0, 2, 1, 3, 4]]
     assert rel_max_err(du2m, du1) <= 1e-13
+
+
+@pytest.mark.parametrize("plane", [(0, 1), (1, 2), (0, 2)])
+def test_3d_rhs_of_extruded_2d_state_equals_pinned_2d_rhs(plane):
+    """Pins the 3D code to Trixi through the 2D code: the 2D Euler EC run reproduces Trixi's published norms to 1e-16
+    (test_oracle_reproduces_trixi_published_norms), and a 3D state that does not depend on the third coordinate must
+    give the 2D rhs! in the plane's variables and zero in the third momentum -- for each of the three coordinate
+    planes, so every direction of the 3D volume / interface / surface code is compared with pinned 2D arithmetic."""
+    a, b = plane
+    c = 3 - a - b
+    o2 = make_oracle(dict(CASES["c2_euler_ec_2d"], level=3))
+    o3 = make_oracle(dict(CASES["c5_euler_ec_3d"], level=3))
+    n = 4
+    E2, E3 = o2.nelements, o3.nelements
+    u2 = o2.compute_coefficients(0.0)
+    # make the 2D state asymmetric (the blast wave alone is symmetric under x <-> y)
+    x2 = o2.f64("node_coordinates").reshape(E2, n, n, 2)
+    U2 = u2.reshape(E2, n, n, 4).copy()
+    U2[..., 0] *= 1.0 + 0.1 * np.sin(0.5 * np.pi * x2[..., 0]) * np.cos(0.25 * np.pi * x2[..., 1])
+    U2[..., 1] += 0.05 * U2[..., 0] * np.cos(0.5 * np.pi * x2[..., 1])
+    du2 = o2.rhs(np.ascontiguousarray(U2).ravel(), 0.0).reshape(E2, n, n, 4)
+    cen2 = o2.f64("cell_centers").reshape(E2, 2)
+    cen3 = o3.f64("cell_centers").reshape(E3, 3)
+    key = {tuple(np.round(cc, 9)): e for e, cc in enumerate(cen2)}
+    e2_of = np.array([key[(round(cc[a], 9), round(cc[b], 9))] for cc in cen3])
+    # node index arrays of the 3D element in (k, j, i) storage order
+    idx = np.meshgrid(np.arange(n), np.arange(n), np.arange(n), indexing="ij")   # idx[0] = k, idx[1] = j, idx[2] = i
+    along = {0: idx[2], 1: idx[1], 2: idx[0]}                                     # node index along axis 0 / 1 / 2
+    i2, j2 = along[a], along[b]
+    src = U2[e2_of][:, j2, i2, :]                      # (E3, k, j, i, 4)
+    dsrc = du2[e2_of][:, j2, i2, :]
+    U3 = np.zeros((E3, n, n, n, 5))
+    U3[..., 0] = src[..., 0]
+    U3[..., 1 + a] = src[..., 1]
+    U3[..., 1 + b] = src[..., 2]
+    U3[..., 4] = src[..., 3]
+    du3 = o3.rhs(np.ascontiguousarray(U3).ravel(), 0.0).reshape(E3, n, n, n, 5)
+    scale = np.abs(du2).max()
+    assert np.abs(du3[..., 0] - dsrc[..., 0]).max() <= 1e-13 * scale
+    assert np.abs(du3[..., 1 + a] - dsrc[..., 1]).max() <= 1e-13 * scale
+    assert np.abs(du3[..., 1 + b] - dsrc[..., 2]).max() <= 1e-13 * scale
+    assert np.abs(du3[..., 4] - dsrc[..., 3]).max() <= 1e-13 * scale
+    assert np.abs(du3[..., 1 + c]).max() <= 1e-13 * scale
