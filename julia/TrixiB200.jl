@@ -136,7 +136,9 @@ function SemidiscretizationHyperbolicGPU(mesh::TreeMesh, equations, initial_cond
         i > 2nd && return Int32(0)
         bc = _bcs isa BoundaryConditionPeriodic ? _bcs : _bcs[i]
         bc isa BoundaryConditionPeriodic ? Int32(0) :
-        bc isa BoundaryConditionDirichlet ? Int32(1) : error("libtrixib200: boundary condition not enumerated")
+        bc isa BoundaryConditionDirichlet ? Int32(1) :
+        bc === Trixi.boundary_condition_slip_wall ? Int32(2) :
+        error("libtrixib200: boundary condition not enumerated")
     end
     adv = equations isa Trixi.AbstractLinearScalarAdvectionEquation ?
           ntuple(i -> i <= nd ? Float64(equations.advection_velocity[i]) : 0.0, 3) : (0.0, 0.0, 0.0)

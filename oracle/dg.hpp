@@ -20,7 +20,7 @@ namespace orc {
 
 enum VolumeIntegralKind { VI_WEAK_FORM = 0, VI_FLUX_DIFFERENCING = 1, VI_SHOCK_CAPTURING_HG = 2 };
 enum IndicatorVariable { IND_DENSITY = 0, IND_PRESSURE = 1, IND_DENSITY_PRESSURE = 2 };
-enum BCKind { BC_PERIODIC = 0, BC_DIRICHLET_IC = 1 };
+enum BCKind { BC_PERIODIC = 0, BC_DIRICHLET_IC = 1, BC_SLIP_WALL = 2 };
 
 struct SolverConfig {
   EqParams eq;
@@ -540,9 +540,13 @@ template <template <class> class EqT> struct Solver : SolverBase {
           for (int v = 0; v < nv; ++v) ui[v] = boundaries_u[(side - 1) + 2 * (v + (size_t)nv * (fn + (size_t)nf * b))];
           double x[3] = {0, 0, 0};
           for (int d = 0; d < nd; ++d) x[d] = c.bd_node_coordinates[d + (size_t)nd * (fn + (size_t)nf * b)];
-          initial_condition(cfg.initial_condition, x, t, cfg.eq, ub);  // BoundaryConditionDirichlet(ic)
-          if (dir % 2 == 0) Eq::two_point(cfg.surface_flux, ui, ub, o, cfg.eq, f);
-          else Eq::two_point(cfg.surface_flux, ub, ui, o, cfg.eq, f);
+          if (cfg.bc[dir - 1] == BC_SLIP_WALL) {
+            Eq::slip_wall_flux(ui, o, dir, cfg.eq, f);   // boundary_condition_slip_wall (compressible Euler)
+          } else {
+            initial_condition(cfg.initial_condition, x, t, cfg.eq, ub);  // BoundaryConditionDirichlet(ic)
+            if (dir % 2 == 0) Eq::two_point(cfg.surface_flux, ui, ub, o, cfg.eq, f);
+            else Eq::two_point(cfg.surface_flux, ub, ui, o, cfg.eq, f);
+          }
           double* s = &surface_flux_values[(size_t)nv * (fn + (size_t)nf * ((dir - 1) + (size_t)2 * nd * e))];
           for (int v = 0; v < nv; ++v) s[v] = f[v];
         }

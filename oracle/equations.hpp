@@ -63,6 +63,7 @@ template <class T> inline T inv_ln_mean(T x, T y) {
 // ---------------------------------------------------------------------------------------------
 template <class T> struct Advection {
   static void flux(const T* u, int o, const EqParams& p, T* f) { f[0] = p.advection_velocity[o - 1] * u[0]; }
+  static bool slip_wall_flux(const T*, int, int, const EqParams&, T*) { return false; }   // Euler only
   static void max_abs_speeds(const T*, const EqParams& p, T* lam) {
     for (int d = 0; d < p.ndim; ++d) lam[d] = std::fabs(p.advection_velocity[d]);
   }
@@ -102,6 +103,27 @@ template <class T> struct Euler {
     for (int d = 0; d < nd; ++d) f[1 + d] = u[o] * q[1 + d];
     f[o] += q[nd + 1];
     f[nd + 1] = (u[nd + 1] + q[nd + 1]) * v;
+  }
+  // boundary_condition_slip_wall on a Cartesian face (Trixi compressible_euler_{1,2,3}d.jl): pressure p* of the wall
+  // Riemann problem (Toro 2009, section 6.3.3) from the velocity along the OUTWARD normal; flux (0, p* e_o, 0).
+  // o: 1-based orientation, direction: 1-based (odd = negative side). [recalled, ORACLE_ASSUMPTIONS.md #13]
+  static bool slip_wall_flux(const T* ui, int o, int direction, const EqParams& p, T* f) {
+    int nd = p.ndim;
+    T q[5];
+    cons2prim(ui, p, q);
+    T rho = q[0], pr = q[nd + 1], vn = q[o];
+    if (direction % 2 == 1) vn = -vn;
+    T ps;
+    if (vn <= 0) {
+      T c = sqrt(p.gamma * pr / rho);
+      ps = pr * pow(1 + 0.5 * (p.gamma - 1) * vn / c, 2 * p.gamma * (1 / (p.gamma - 1)));
+    } else {
+      T A = 2 / ((p.gamma + 1) * rho), B = pr * (p.gamma - 1) / (p.gamma + 1);
+      ps = pr + 0.5 * vn / A * (vn + sqrt(vn * vn + 4 * A * (pr + B)));
+    }
+    for (int v = 0; v < nd + 2; ++v) f[v] = 0;
+    f[o] = ps;
+    return true;
   }
   static void max_abs_speeds(const T* u, const EqParams& p, T* lam) {
     T q[5];
@@ -240,6 +262,7 @@ template <class T> struct Mhd3D {
     T bo = (o == 1) ? b1 : (o == 2 ? b2 : b3);
     return sqrt(0.5 * (a_square + b_square) + 0.5 * sqrt(sq(a_square + b_square) - 4.0 * a_square * bo * bo));
   }
+  static bool slip_wall_flux(const T*, int, int, const EqParams&, T*) { return false; }   // Euler only
   static void max_abs_speeds(const T* u, const EqParams& p, T* lam) {
     for (int d = 0; d < 3; ++d) lam[d] = fabs(u[1 + d] / u[0]) + fast_wavespeed(u, d + 1, p);
   }

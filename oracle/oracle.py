@@ -22,7 +22,7 @@ VI = {"weak_form": 0, "flux_differencing": 1, "shock_capturing_hg": 2}
 IC = {"constant": 0, "convergence_test": 1, "weak_blast_wave": 2, "density_wave": 3}
 SRC = {"none": 0, "convergence_test": 1}
 IND = {"density": 0, "pressure": 1, "density_pressure": 2}
-BC = {"periodic": 0, "dirichlet_ic": 1}
+BC = {"periodic": 0, "dirichlet_ic": 1, "slip_wall": 2}
 
 
 class OrcConfig(C.Structure):

@@ -75,6 +75,13 @@ CASES = {
     "euler_fd_nonperiodic_3d": case(3, "euler", level=2, vi="flux_differencing", volume_flux="flux_ranocha",
                                     surface_flux="flux_lax_friedrichs", source="convergence_test", bc="dirichlet_ic",
                                     periodic=False, cmin=0.0, cmax=2.0),
+    # closed boxes with boundary_condition_slip_wall: line-owner kernel with given wall
+    # fluxes, and the 2D weak form
+    "euler_slip_wall_3d": case(3, "euler", level=2, vi="flux_differencing", volume_flux="flux_ranocha",
+                               surface_flux="flux_lax_friedrichs", ic="weak_blast_wave", bc="slip_wall", periodic=False,
+                               cmin=-2.0, cmax=2.0),
+    "euler_slip_wall_2d": case(2, "euler", level=3, surface_flux="flux_hll", ic="weak_blast_wave", bc="slip_wall",
+                               periodic=False, cmin=-2.0, cmax=2.0),
     # other polynomial degrees go through the staged kernels
     "euler_ec_3d_p2": case(3, "euler", level=2, polydeg=2, vi="flux_differencing", volume_flux="flux_ranocha",
                            surface_flux="flux_ranocha", ic="weak_blast_wave", cmin=-2.0, cmax=2.0),
@@ -137,7 +144,9 @@ def make_semi(c, level=None, staged_only=False, **kw):
           "weak_blast_wave": T.initial_condition_weak_blast_wave,
           "density_wave": T.initial_condition_density_wave}[c["ic"]]
     src = T.source_terms_convergence_test if c["source"] == "convergence_test" else None
-    bc = T.boundary_condition_periodic if c["bc"] == "periodic" else T.BoundaryConditionDirichlet(ic)
+    bc = {"periodic": T.boundary_condition_periodic, "slip_wall": T.boundary_condition_slip_wall}.get(c["bc"])
+    if bc is None:
+        bc = T.BoundaryConditionDirichlet(ic)
     return T.SemidiscretizationHyperbolicGPU(mesh, eq, ic, solver, source_terms=src, boundary_conditions=bc,
                                              staged_only=staged_only, **kw)
 

@@ -270,3 +270,50 @@ def test_3d_rhs_of_extruded_2d_state_equals_pinned_2d_rhs(plane):
     assert np.abs(du3[..., 1 + b] - dsrc[..., 2]).max() <= 1e-13 * scale
     assert np.abs(du3[..., 4] - dsrc[..., 3]).max() <= 1e-13 * scale
     assert np.abs(du3[..., 1 + c]).max() <= 1e-13 * scale
+
+
+def _moving_state(o, c, seed=2):
+    """IC with a smooth nonzero velocity field everywhere (the walls see both signs of the normal velocity)."""
+    nd, nv = c["ndim"], o.nvars
+    E, n = o.nelements, 4
+    x = o.f64("node_coordinates").reshape((E,) + (n,) * nd + (nd,))
+    u = o.compute_coefficients(0.0).reshape((E,) + (n,) * nd + (nv,)).copy()
+    rho = u[..., 0]
+    ke_old = 0.5 * (u[..., 1:1 + nd] ** 2).sum(-1) / rho
+    for d in range(nd):
+        u[..., 1 + d] = rho * 0.3 * np.sin(0.7 * (d + 1) + 0.9 * x[..., d] + 0.4 * x[..., (d + 1) % nd])
+    u[..., nd + 1] += 0.5 * (u[..., 1:1 + nd] ** 2).sum(-1) / rho - ke_old
+    return u
+
+
+@pytest.mark.parametrize("name", ["euler_slip_wall_3d", "euler_slip_wall_2d"])
+def test_slip_wall_box_conserves_mass_and_energy(name):
+    """boundary_condition_slip_wall: the wall flux is (0, p* e_o, 0), so total mass and total energy of a closed box do
+    not change whatever the state; the momentum of the box does (wall pressure)."""
+    c = CASES[name]
+    o = make_oracle(c)
+    u = _moving_state(o, c)
+    du = o.rhs(np.ascontiguousarray(u).ravel(), 0.0)
+    rate = o.integrate(du)
+    scale = o.integrate(np.abs(du))
+    nd = c["ndim"]
+    assert abs(rate[0]) <= 1e-13 * scale[0] and abs(rate[nd + 1]) <= 1e-13 * scale[nd + 1]
+    assert np.abs(rate[1:1 + nd]).max() > 1e-6           # the walls do push
+
+
+def test_slip_wall_mirror_symmetry_3d():
+    """Mirroring the state in x (x -> -x, v1 -> -v1) mirrors du: the -x and +x walls (odd / even direction, opposite
+    outward normals, both branches of the wall Riemann problem) must treat mirrored states alike."""
+    c = CASES["euler_slip_wall_3d"]
+    o = make_oracle(c)
+    E, n, nv = o.nelements, 4, 5
+    u = _moving_state(o, c)                                  # [e, k, j, i, v]
+    cen = o.f64("cell_centers").reshape(E, 3)
+    key = {tuple(np.round(cc, 9)): e for e, cc in enumerate(cen)}
+    perm = np.array([key[(round(-cc[0], 9), round(cc[1], 9), round(cc[2], 9))] for cc in cen])
+    sign = np.array([1.0, -1.0, 1.0, 1.0, 1.0])
+    um = u[perm][:, :, :, ::-1, :] * sign                    # element at -cx, node order reversed in x, v1 flipped
+    du = o.rhs(np.ascontiguousarray(u).ravel(), 0.0).reshape(E, n, n, n, nv)
+    dum = o.rhs(np.ascontiguousarray(um).ravel(), 0.0).reshape(E, n, n, n, nv)
+    back = dum[perm][:, :, :, ::-1, :] * sign
+    assert rel_max_err(back, du) <= 1e-13

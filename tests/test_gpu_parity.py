@@ -268,6 +268,23 @@ def test_full_run_device_analysis():
     assert abs(l2[0] - 6.0388296447998465e-6) <= 1e-10 and abs(linf[0] - 3.217887726258972e-5) <= 1e-10
 
 
+@pytest.mark.parametrize("kernel", ["staged", "fused"])
+@pytest.mark.parametrize("name", ["euler_slip_wall_3d", "euler_slip_wall_2d"])
+def test_slip_wall_with_moving_state(name, kernel):
+    """boundary_condition_slip_wall with nonzero normal velocity at every wall (both branches of the wall Riemann
+    problem, both outward normals): du against the oracle, staged kernels and the fused path (3D: line-owner kernel
+    consuming the wall fluxes from surface_flux_values)."""
+    from test_cpu_oracle import _moving_state
+    c = CASES[name]
+    o = make_oracle(c)
+    semi = make_semi(c, staged_only=(kernel == "staged"))
+    u = np.ascontiguousarray(_moving_state(o, c)).ravel()
+    du_ref = o.rhs(u, 0.0)
+    du_d = semi.new_vector().fill_(float("nan"))
+    semi.rhs(du_d, _to_dev(semi, u), 0.0)
+    assert rel_max_err(du_d.cpu().numpy(), du_ref) <= TOL
+
+
 def test_large_mesh_properties():
     """Size-independent properties at a size the oracle would not finish in seconds (3D Euler EC, level 5,
     2.1 M DOF): free-stream preservation, discrete conservation and entropy conservation of the EC scheme."""

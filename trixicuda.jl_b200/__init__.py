@@ -17,7 +17,8 @@ from .equations import (
     min_max_speed_naive, min_max_speed_davis, min_max_speed_einfeldt,
     initial_condition_constant, initial_condition_convergence_test, initial_condition_weak_blast_wave,
     initial_condition_density_wave, InitialCondition,
-    boundary_condition_periodic, BoundaryConditionDirichlet, source_terms_convergence_test,
+    boundary_condition_periodic, boundary_condition_slip_wall, BoundaryConditionDirichlet,
+    source_terms_convergence_test,
     density, pressure, density_pressure,
 )
 from .solver import (DGSEMGPU, SurfaceIntegralWeakForm, VolumeIntegralWeakForm, VolumeIntegralFluxDifferencing,

@@ -23,7 +23,7 @@ FLUX = {"flux_central": 0, "flux_lax_friedrichs": 1, "flux_lax_friedrichs_naive"
         "flux_hlle": 8}
 VI_WEAK_FORM, VI_FLUX_DIFFERENCING, VI_SHOCK_CAPTURING_HG = 0, 1, 2
 IND = {"density": 0, "pressure": 1, "density_pressure": 2}
-BC_PERIODIC, BC_DIRICHLET_IC = 0, 1
+BC_PERIODIC, BC_DIRICHLET_IC, BC_SLIP_WALL = 0, 1, 2
 IC = {"constant": 0, "convergence_test": 1, "weak_blast_wave": 2, "density_wave": 3}
 SRC = {"none": 0, "convergence_test": 1}
 FLAG_STAGED_ONLY = 1

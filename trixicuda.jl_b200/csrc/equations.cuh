@@ -85,6 +85,7 @@ template <int ND> struct EqAdvection {
   TB_D static void two_point_qf(int kind, const double* ql, const double* qr, int o, const EqPrm& p, double* f) {
     two_point(kind, ql, qr, o, p, f);
   }
+  TB_D static bool slip_wall_flux(const double*, int, int, const EqPrm&, double*) { return false; }   // Euler only
   TB_D static void max_abs_speeds(const double*, const EqPrm& p, double* lam) {
 #pragma unroll
     for (int d = 0; d < ND; ++d) lam[d] = fabs(p.a[d]);
@@ -127,6 +128,29 @@ template <int ND> struct EqEuler {
 #pragma unroll
     for (int d = 0; d < ND; ++d) { u[1 + d] = q[0] * q[1 + d]; ke += u[1 + d] * q[1 + d]; }
     u[ND + 1] = q[ND + 1] / (p.gamma - 1) + 0.5 * ke;
+  }
+  // boundary_condition_slip_wall on a Cartesian face (Trixi compressible_euler_{1,2,3}d.jl, called with the contract of
+  // reference src/solvers/dg_3d_kernel.jl:1327-1343): pressure p* of the wall Riemann problem (Toro 2009, section
+  // 6.3.3) from the velocity along the OUTWARD normal; the flux is (0, p* e_o, 0) on either side. o: 1-based
+  // orientation, dir: 0-based direction (even = negative side). Returns true (handled).
+  TB_D static bool slip_wall_flux(const double* ui, int o, int dir, const EqPrm& p, double* f) {
+    double q[NV];
+    cons2prim(ui, p, q);
+    const double rho = q[0], pr = q[ND + 1];
+    double vn = osel(q, o);
+    if ((dir & 1) == 0) vn = -vn;
+    double ps;
+    if (vn <= 0) {
+      const double c = sqrt(p.gamma * pr / rho);
+      ps = pr * pow(1 + 0.5 * (p.gamma - 1) * vn / c, 2 * p.gamma * p.inv_gm1);
+    } else {
+      const double A = 2 / ((p.gamma + 1) * rho), B = pr * (p.gamma - 1) / (p.gamma + 1);
+      ps = pr + 0.5 * vn / A * (vn + sqrt(vn * vn + 4 * A * (pr + B)));
+    }
+#pragma unroll
+    for (int v = 0; v < NV; ++v) f[v] = 0;
+    f[o] = ps;
+    return true;
   }
   TB_D static void flux(const double* u, int o, const EqPrm& p, double* f) {
     double q[NV];
@@ -536,6 +560,7 @@ struct EqMhd3 {
     f[5] = v1 * Bo_rr; f[6] = v2 * Bo_rr; f[7] = v3 * Bo_rr;
     f[8] = vo * psi_rr;
   }
+  TB_D static bool slip_wall_flux(const double*, int, int, const EqPrm&, double*) { return false; }   // Euler only
   TB_D static void max_abs_speeds(const double* u, const EqPrm& p, double* lam) {
 #pragma unroll
     for (int d = 0; d < 3; ++d) lam[d] = fabs(u[1 + d] / u[0]) + fast_wavespeed(u, d + 1, p);

@@ -284,10 +284,14 @@ __global__ void k_boundary_flux(Dev d, double t) {
   for (int v = 0; v < NV; ++v) ui[v] = d.boundaries_u[(side - 1) + 2 * (v + (size_t)NV * (f + (size_t)nf * b))];
 #pragma unroll
   for (int q = 0; q < ND; ++q) x[q] = d.bd_coords[q + (size_t)ND * (f + (size_t)nf * b)];
-  // BoundaryConditionDirichlet(initial_condition): call contract reference dg_3d_kernel.jl:1327-1343
-  Eq::initial_condition(d.ic, x, t, d.prm, ub);
-  if (dir % 2 == 1) Eq::two_point(d.surf_flux, ui, ub, dim + 1, d.prm, fl);
-  else Eq::two_point(d.surf_flux, ub, ui, dim + 1, d.prm, fl);
+  if (d.bc[dir] == TRIXIB200_BC_SLIP_WALL) {
+    Eq::slip_wall_flux(ui, dim + 1, dir, d.prm, fl);   // create() admits it for compressible Euler only
+  } else {
+    // BoundaryConditionDirichlet(initial_condition): call contract reference dg_3d_kernel.jl:1327-1343
+    Eq::initial_condition(d.ic, x, t, d.prm, ub);
+    if (dir % 2 == 1) Eq::two_point(d.surf_flux, ui, ub, dim + 1, d.prm, fl);
+    else Eq::two_point(d.surf_flux, ub, ui, dim + 1, d.prm, fl);
+  }
   double* s = d.sfv + (size_t)NV * (f + (size_t)nf * (dir + (size_t)2 * ND * e));
 #pragma unroll
   for (int v = 0; v < NV; ++v) s[v] = fl[v];

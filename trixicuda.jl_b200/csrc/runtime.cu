@@ -375,6 +375,12 @@ static int create_impl(const trixib200_config* cfg, const trixib200_basis_host* 
     return fail(TRIXIB200_EUNSUPPORTED, "source_terms_convergence_test only for compressible Euler");
   if (c.nranks < 1 || c.rank < 0 || c.rank >= c.nranks) return fail(TRIXIB200_EINVAL, "bad rank/nranks");
   if (ms->nelements < c.nranks) return fail(TRIXIB200_EINVAL, "fewer elements than ranks");
+  for (int q = 0; q < 2 * c.ndim; ++q) {
+    const int bc = c.boundary_conditions[q];
+    if (bc < TRIXIB200_BC_PERIODIC || bc > TRIXIB200_BC_SLIP_WALL) return fail(TRIXIB200_EUNSUPPORTED, "unknown boundary condition id");
+    if (bc == TRIXIB200_BC_SLIP_WALL && c.equations != TRIXIB200_EQ_EULER)
+      return fail(TRIXIB200_EUNSUPPORTED, "boundary_condition_slip_wall only for compressible Euler");
+  }
   if (c.nranks > 1 && ms->nmortars > 0) return fail(TRIXIB200_EUNSUPPORTED, "multi-GPU with mortars is not supported yet");
   if (c.nranks > 1 && c.volume_integral == TRIXIB200_VI_SHOCK_CAPTURING_HG && c.alpha_smooth)
     return fail(TRIXIB200_EUNSUPPORTED, "multi-GPU shock capturing with alpha_smooth is not supported yet");

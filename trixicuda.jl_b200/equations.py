@@ -296,6 +296,9 @@ class BoundaryConditionDirichlet(_Named):
         self.boundary_value_function = boundary_value_function
 
 
+# `boundary_condition_slip_wall` (compressible Euler): enumerated, evaluated on the device
+boundary_condition_slip_wall = _Named("boundary_condition_slip_wall", _lib.BC_SLIP_WALL)
+
 source_terms_convergence_test = _Named("source_terms_convergence_test", _lib.SRC["convergence_test"])
 
 # indicator variables

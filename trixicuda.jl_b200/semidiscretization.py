@@ -15,7 +15,8 @@ from dataclasses import dataclass
 import numpy as np
 
 from . import _lib
-from .equations import (InitialCondition, BoundaryConditionDirichlet, boundary_condition_periodic)
+from .equations import (InitialCondition, BoundaryConditionDirichlet, boundary_condition_periodic,
+                        boundary_condition_slip_wall)
 from .solver import solver_enums
 from .treemesh import TreeMesh, init_containers
 
@@ -66,6 +67,8 @@ class SemidiscretizationHyperbolicGPU:
             elif isinstance(bc, BoundaryConditionDirichlet):
                 cfg.boundary_conditions[i] = _lib.BC_DIRICHLET_IC
                 ic_for_bc = bc.boundary_value_function
+            elif bc is boundary_condition_slip_wall:
+                cfg.boundary_conditions[i] = _lib.BC_SLIP_WALL
             else:
                 raise NotImplementedError(f"boundary condition {bc!r} is not enumerated in libtrixib200")
         ic = self.initial_condition
