@@ -43,11 +43,17 @@ __device__ __noinline__ L3Vec5 l6_pair_correction(L6Pair p, double inv_gm1) {
 __device__ constexpr int L6_PA[8] = {0, 1, 1, 1, 2, 2, 3, 4};
 __device__ constexpr int L6_PB[8] = {1, 2, 3, 4, 3, 4, 4, 5};
 
+// high word of 1e-4: f2 >= 1e-4 decided on the high words (both branches of the means are accurate near the threshold;
+// NaN compares as "rough"; f2, g2 are squares, so the unsigned comparison is the ordering of the doubles)
+constexpr unsigned L6_ROUGH_HI = 0x3F1A36E2u;
+
 // NP two-point fluxes (orientation 1 in the rotated frame) of the pairs K0 .. K0 + NP - 1, staged across the pairs so
-// that consecutive instructions are independent. Returns the "needs the logarithmic branch" mask (bit k - K0).
+// that consecutive instructions are independent. hw[k] = larger high word of the two squared relative jumps of pair k:
+// the pair needs the logarithmic branch iff hw[k] >= L6_ROUGH_HI (one integer max per pair on the hot path; the caller
+// reduces them to ONE comparison per batch).
 template <bool FAST, int K0, int NP>
-TB_D unsigned l6_fluxes(const double (&Q)[6][5], int vflux, int sflux, const EqPrm& prm, double (&F)[NP][5]) {
-  unsigned rough = 0;
+TB_D void l6_fluxes(const double (&Q)[6][5], int vflux, int sflux, const EqPrm& prm, double (&F)[NP][5],
+                    unsigned (&hw)[NP]) {
   if (FAST) {
     double s[NP], r[NP], dd[NP], tt[NP], rt[NP], xy[NP], rm[NP], im[NP];
 #pragma unroll
@@ -73,7 +79,7 @@ TB_D unsigned l6_fluxes(const double (&Q)[6][5], int vflux, int sflux, const EqP
       const double ut = xy[k] * rt[k], g2 = ut * ut;
       rm[k] = s[k] * fma(f2, fma(f2, fma(f2, -22.0 / 945, -2.0 / 45), -1.0 / 6), 0.5);
       im[k] = ((Q[L6_PA[K0 + k]][4] * Q[L6_PB[K0 + k]][4]) * rt[k]) * fma(g2, fma(g2, fma(g2, 2.0 / 7, 2.0 / 5), 2.0 / 3), 2.0);
-      if (l3_is_rough(f2) || l3_is_rough(g2)) rough |= 1u << k;
+      hw[k] = max((unsigned)__double2hiint(f2), (unsigned)__double2hiint(g2));
     }
 #pragma unroll
     for (int k = 0; k < NP; ++k)
@@ -83,9 +89,9 @@ TB_D unsigned l6_fluxes(const double (&Q)[6][5], int vflux, int sflux, const EqP
     for (int k = 0; k < NP; ++k) {
       const bool surf = (K0 + k == 0) || (K0 + k == 7);
       l3_flux<1, -1>(surf ? sflux : vflux, Q[L6_PA[K0 + k]], Q[L6_PB[K0 + k]], prm, F[k]);
+      hw[k] = 0;
     }
   }
-  return rough;
 }
 
 // Fused low-storage Runge-Kutta stage (2N scheme, e.g. CarpenterKennedy2N54): instead of writing du the x phase does
@@ -351,17 +357,21 @@ k_line6(const __grid_constant__ Dev d, const __grid_constant__ LineOps ops, doub
         constexpr int K0 = decltype(k0_tag)::value;
         if (K0 + NP > 7) l3_to_q(nbv[1], gm1, Q[5]);   // converted when its pair comes up
         double F[NP][NV];
-        unsigned rough = l6_fluxes<FAST, K0, NP>(Q, vflux, sflux, prm, F);
+        unsigned hw[NP];
+        l6_fluxes<FAST, K0, NP>(Q, vflux, sflux, prm, F, hw);
         if (SFV && K0 == 0) {
-          if (sfv_lo) rough &= ~1u;
+          if (sfv_lo) hw[0] = 0;      // the trace IS the flux: nothing to correct
 #pragma unroll
           for (int v = 0; v < NV; ++v) F[0][v] = sfv_lo ? nbv[0][v] : F[0][v];
         }
         if (SFV && K0 + NP > 7) {
-          if (sfv_hi) rough &= ~(1u << (7 - K0));
+          if (sfv_hi) hw[7 - K0] = 0;
 #pragma unroll
           for (int v = 0; v < NV; ++v) F[7 - K0][v] = sfv_hi ? nbv[1][v] : F[7 - K0][v];
         }
+        unsigned worst = hw[0];
+#pragma unroll
+        for (int k = 1; k < NP; ++k) worst = max(worst, hw[k]);
         if (K0 <= 1 && K0 + NP > 1) load_old(1, acc[1]);
         if (K0 <= 2 && K0 + NP > 2) load_old(2, acc[2]);
         if (K0 <= 3 && K0 + NP > 3) load_old(3, acc[3]);
@@ -379,10 +389,10 @@ k_line6(const __grid_constant__ Dev d, const __grid_constant__ LineOps ops, doub
         for (int k = 0; k < NP; ++k)
 #pragma unroll
           for (int v = 0; v < NV; ++v) accumulate(k, v);
-        if (FAST && rough != 0) {
+        if (FAST && worst >= L6_ROUGH_HI) {
 #pragma unroll
           for (int k = 0; k < NP; ++k)
-            if (rough & (1u << k)) {
+            if (hw[k] >= L6_ROUGH_HI) {
               const int kk = K0 + k;
               L6Pair pp;
 #pragma unroll
