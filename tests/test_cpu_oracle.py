@@ -317,3 +317,24 @@ def test_slip_wall_mirror_symmetry_3d():
     dum = o.rhs(np.ascontiguousarray(um).ravel(), 0.0).reshape(E, n, n, n, nv)
     back = dum[perm][:, :, :, ::-1, :] * sign
     assert rel_max_err(back, du) <= 1e-13
+
+
+def test_mhd_with_zero_field_reduces_to_pinned_euler():
+    """flux_hindenlang_gassner extends flux_ranocha to GLM-MHD: with B = 0 and psi = 0 the MHD rhs! (volume, interface
+    and surface terms, nonconservative Powell terms included) must be the Euler rhs! in (rho, rho v, rho e) and leave B
+    and psi untouched. Ties the MHD code path to the Euler path, which is pinned to Trixi's published norms."""
+    cm = dict(CASES["mhd_ec_3d"])
+    ce = dict(CASES["c5_euler_ec_3d"], level=cm["level"])
+    om, oe = make_oracle(cm), make_oracle(ce)
+    assert cm["gamma"] == ce["gamma"] and om.nelements == oe.nelements
+    rng = np.random.default_rng(1)
+    u5 = oe.compute_coefficients(0.0).reshape(-1, 5).copy()
+    u5[:, 0] *= 1 + 0.1 * rng.uniform(-1, 1, len(u5))
+    u5[:, 1:4] += 0.1 * rng.uniform(-1, 1, (len(u5), 3))
+    u5[:, 4] *= 1 + 0.1 * rng.uniform(0, 1, len(u5))
+    u9 = np.zeros((len(u5), 9))
+    u9[:, :5] = u5
+    du5 = oe.rhs(np.ascontiguousarray(u5).ravel(), 0.0).reshape(-1, 5)
+    du9 = om.rhs(np.ascontiguousarray(u9).ravel(), 0.0).reshape(-1, 9)
+    assert np.abs(du9[:, :5] - du5).max() <= 1e-13 * np.abs(du5).max()
+    assert np.abs(du9[:, 5:]).max() == 0.0
