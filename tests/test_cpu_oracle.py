@@ -338,3 +338,31 @@ def test_mhd_with_zero_field_reduces_to_pinned_euler():
     du9 = om.rhs(np.ascontiguousarray(u9).ravel(), 0.0).reshape(-1, 9)
     assert np.abs(du9[:, :5] - du5).max() <= 1e-13 * np.abs(du5).max()
     assert np.abs(du9[:, 5:]).max() == 0.0
+
+
+def test_2d_rhs_of_extruded_1d_state_equals_1d_rhs():
+    """The 1D Euler EC code against the Trixi-pinned 2D code: a 2D state that does not depend on y gives the 1D rhs! in
+    (rho, rho v1, rho e) and zero in rho v2."""
+    o1 = make_oracle(dict(CASES["euler_ec_1d"], level=3))
+    o2 = make_oracle(dict(CASES["c2_euler_ec_2d"], level=3))
+    n, E1, E2 = 4, o1.nelements, o2.nelements
+    x1 = o1.f64("node_coordinates").reshape(E1, n)
+    U1 = o1.compute_coefficients(0.0).reshape(E1, n, 3).copy()
+    U1[..., 0] *= 1.0 + 0.1 * np.sin(0.5 * np.pi * x1)
+    U1[..., 1] += 0.1 * U1[..., 0] * np.cos(0.25 * np.pi * x1)
+    du1 = o1.rhs(np.ascontiguousarray(U1).ravel(), 0.0).reshape(E1, n, 3)
+    cen1 = o1.f64("cell_centers").reshape(E1)
+    cen2 = o2.f64("cell_centers").reshape(E2, 2)
+    key = {round(float(cc), 9): e for e, cc in enumerate(cen1)}
+    e1_of = np.array([key[round(float(cc[0]), 9)] for cc in cen2])
+    U2 = np.zeros((E2, n, n, 4))                      # [e, j, i, v]
+    src, dsrc = U1[e1_of], du1[e1_of]                 # (E2, i, 3)
+    U2[..., 0] = src[:, None, :, 0]
+    U2[..., 1] = src[:, None, :, 1]
+    U2[..., 3] = src[:, None, :, 2]
+    du2 = o2.rhs(np.ascontiguousarray(U2).ravel(), 0.0).reshape(E2, n, n, 4)
+    scale = np.abs(du1).max()
+    assert np.abs(du2[..., 0] - dsrc[:, None, :, 0]).max() <= 1e-13 * scale
+    assert np.abs(du2[..., 1] - dsrc[:, None, :, 1]).max() <= 1e-13 * scale
+    assert np.abs(du2[..., 3] - dsrc[:, None, :, 2]).max() <= 1e-13 * scale
+    assert np.abs(du2[..., 2]).max() <= 1e-13 * scale
