@@ -40,7 +40,7 @@ def run(n_units, unit_gb, ready_after):
         ua, da = up_i < n_units, dl_left > 0
         ru = (50.0 if da else 55.5) if ua else 0.0
         rd = (50.0 if ua else 57.2) if da else 0.0
-        dt = min([up_left / ru] * ua + [dl_left / rd] * da)
+        dt = min(([up_left / ru] if ua else []) + ([dl_left / rd] if da else []))
         t += dt
         if ua:
             up_left -= ru * dt
