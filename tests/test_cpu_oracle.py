@@ -22,34 +22,50 @@ NORMS = json.load(open(os.path.join(GOLDEN_DIR, "trixi_regression_norms.json")))
 
 def _oracle_for(entry):
     nd = entry["ndim"]
-    kw = dict(ndim=nd, equations=entry["equations"], polydeg=3, initial_refinement_level=entry["level"])
+    kw = dict(ndim=nd, equations=entry["equations"], polydeg=entry.get("polydeg", 3),
+              initial_refinement_level=entry["level"])
     if entry["equations"] == "advection":
         kw.update(advection_velocity=tuple(entry["advection_velocity"]), coordinates_min=(-1.0,) * 3,
-                  coordinates_max=(1.0,) * 3)
+                  coordinates_max=(1.0,) * 3,
+                  refinement_patches=[(tuple(lo), tuple(hi)) for lo, hi in entry.get("refinement_patches", [])])
     else:
-        kw.update(volume_integral="flux_differencing", volume_flux="flux_ranocha", surface_flux="flux_ranocha",
-                  initial_condition="weak_blast_wave", coordinates_min=(-2.0,) * 3, coordinates_max=(2.0,) * 3)
+        kw.update(volume_integral=entry.get("volume_integral", "flux_differencing" if "source" not in entry
+                                            else "weak_form"),
+                  volume_flux=entry.get("volume_flux", "flux_ranocha"),
+                  volume_flux_fv=entry.get("volume_flux_fv", "flux_lax_friedrichs"),
+                  surface_flux=entry.get("surface_flux", "flux_ranocha"),
+                  initial_condition=entry.get("initial_condition", "weak_blast_wave"),
+                  source=entry.get("source", "none"),
+                  coordinates_min=(entry.get("coordinates_min", -2.0),) * 3,
+                  coordinates_max=(entry.get("coordinates_max", 2.0),) * 3)
     return O.Oracle(**kw)
 
 
 @pytest.mark.parametrize("name", sorted(n for n, e in NORMS.items() if e.get("gate", True)))
 def test_oracle_reproduces_trixi_published_norms(name):
+    """Full runs (rhs!, CK2N54, StepsizeCallback, analyzer) against Trixi.jl's published l2 / linf."""
     e = NORMS[name]
     o = _oracle_for(e)
     u, _ = o.solve(o.compute_coefficients(0.0), 0.0, e["tend"], cfl=e["cfl"])
     l2, linf = o.error_norms(u, e["tend"])
-    assert np.abs(l2 - np.array(e["l2"])).max() <= 1e-12, (l2.tolist(), e["l2"])
+    assert e["l2"] is not None or e["linf"] is not None
+    if e["l2"] is not None:
+        assert np.abs(l2 - np.array(e["l2"])).max() <= e.get("tol_l2", 1e-12), (l2.tolist(), e["l2"])
     if e["linf"] is not None:
-        assert np.abs(linf - np.array(e["linf"])).max() <= 1e-11, (linf.tolist(), e["linf"])
+        assert np.abs(linf - np.array(e["linf"])).max() <= e.get("tol_linf", 1e-11), (linf.tolist(), e["linf"])
 
 
-def test_ungated_recalled_norms_are_close():
-    """Low-confidence recalled digits are only required to agree to 2 %, documenting the gap (see the JSON note)."""
-    e = NORMS["euler_ec_3d"]
+@pytest.mark.parametrize("name", sorted(n for n, e in NORMS.items() if not e.get("gate", True)))
+def test_ungated_recalled_norms_are_close(name):
+    """The two 3D weak-blast-wave entries (EC, shock capturing) are UNRESOLVED: the oracle sits 0.3-0.7 % (l2) above the
+    recalled digits in both. Documented here with a band so that a change of the gap is noticed."""
+    e = NORMS[name]
     o = _oracle_for(e)
     u, _ = o.solve(o.compute_coefficients(0.0), 0.0, e["tend"], cfl=e["cfl"])
-    l2, _ = o.error_norms(u, e["tend"])
-    assert np.abs(l2 / np.array(e["l2"]) - 1).max() <= 0.02
+    l2, linf = o.error_norms(u, e["tend"])
+    r = l2 / np.array(e["l2"]) - 1
+    assert 0.002 <= r.min() and r.max() <= 0.008, r
+    assert np.abs(linf / np.array(e["linf"]) - 1).max() <= 0.03
 
 
 def _golden_names():
@@ -366,3 +382,36 @@ def test_2d_rhs_of_extruded_1d_state_equals_1d_rhs():
     assert np.abs(du2[..., 1] - dsrc[:, None, :, 1]).max() <= 1e-13 * scale
     assert np.abs(du2[..., 3] - dsrc[:, None, :, 2]).max() <= 1e-13 * scale
     assert np.abs(du2[..., 2]).max() <= 1e-13 * scale
+
+
+# -------------------------------------------------------------------- independent restatement (3D Euler EC)
+def test_oracle_equals_independent_numpy_restatement_3d_euler_ec():
+    """rhs!, max_dt, the full CK2N54 run and the analyzer of examples/euler_ec_3d.jl (level 3, cfl 1.3, t = 0.4) computed by
+    tests/independent_dgsem3d.py agree with the oracle to round-off: the 0.6 % gap to the recalled Trixi digits
+    (trixi_regression_norms.json:euler_ec_3d) is not a 3D-only slip of the oracle's containers, loops or analyzer."""
+    import independent_dgsem3d as I
+    e = NORMS["euler_ec_3d"]
+    o = _oracle_for(e)
+    g = I.UniformPeriodic3D(e["level"])
+    ne = o.nelements
+    centers = o.f64("node_coordinates").reshape(ne, 4, 4, 4, 3).mean(axis=(1, 2, 3))
+    perm = g.morton_permutation(centers)
+    u0 = o.compute_coefficients(0.0)
+    ug = I.weak_blast_wave(g.x)
+    uo0 = u0.reshape(ne, 4, 4, 4, 5)[perm]
+    assert np.array_equal(ug[..., 0], uo0[..., 0])                     # the same nodes lie inside the blast
+    assert np.abs(ug - uo0).max() <= 1e-15
+
+    def from_grid(a):
+        out = np.empty((ne, 4, 4, 4, 5))
+        out[perm] = a
+        return out.ravel()
+
+    assert rel_max_err(from_grid(g.rhs(ug)), o.rhs(u0)) <= 1e-14
+    assert abs(g.max_dt(ug) / o.max_dt(u0) - 1) <= 1e-15
+    uo, steps_o = o.solve(u0, 0.0, e["tend"], cfl=e["cfl"])
+    un, steps_n = g.solve(ug, e["tend"], e["cfl"])
+    assert steps_o == steps_n == 11
+    l2o, linfo = o.error_norms(uo, e["tend"])
+    l2n, linfn = g.error_norms(un, I.weak_blast_wave)
+    assert np.abs(l2n - l2o).max() <= 1e-13 and np.abs(linfn - linfo).max() <= 1e-12
