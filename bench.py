@@ -1,19 +1,24 @@
 #!/usr/bin/env python
-"""bench.py -- rhs! DOF-updates/s (1/PID) of the TreeMesh DGSEM hot path, BASELINE.json config 5:
-3D compressible Euler, entropy-conserving flux differencing (flux_ranocha volume + surface), polydeg 3,
-TreeMesh refinement level 7 (2 097 152 elements, 134 217 728 DOF per field), periodic, weak-blast-wave IC
-(reference examples/euler_ec_3d.jl:9-21 at level 7; method: reference benchmark/euler_ec_3d.jl:56-72).
+"""bench.py -- rhs! DOF-updates/s (1/PID) of the TreeMesh DGSEM hot path.
 
-A "step" is ONE rhs!(du, u, semi, t) over the whole mesh. `value` = ndofs_global * steps / device time with u
-resident in HBM; `e2e` = the same through the host-vector entry point (trixib200_rhs_host: pinned host u ->
-device, rhs!, du -> pinned host) each step. N > 1: the SAME level-7 mesh is partitioned along the Morton curve
-over the ranks ("scaling": "strong"), halo-face traces go over NCCL send/recv inside rhs!.
+Default workload = BASELINE.json configs[4] ("config 5"): 3D compressible Euler, entropy-conserving flux differencing
+(flux_ranocha volume + surface), polydeg 3, TreeMesh refinement level 7 (2 097 152 elements, 134 217 728 DOF per
+field), periodic, weak-blast-wave IC (reference examples/euler_ec_3d.jl:9-21 at level 7; method: reference
+benchmark/euler_ec_3d.jl:56-72). `--config 1..4` times the other BASELINE.json configs on one GPU (they are L2-resident:
+L2 is flushed between timed calls and every call is timed on its own).
 
-    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl reference] [--level L]
+A "step" is ONE rhs!(du, u, semi, t) over the whole mesh. `value` = ndofs_global * steps / device time with u resident
+in HBM; `e2e` = the same through the host-vector entry point (trixib200_rhs_host: pinned host u -> device, rhs!, du ->
+pinned host) each step. N > 1: the SAME mesh is partitioned along the Morton curve over the ranks ("scaling":
+"strong"; `--weak` raises the level so that every rank keeps a level-7 share), halo-face traces go from GPU to GPU
+inside rhs!. Before timing, du of the product is compared with the CPU oracle (`parity` in the line), and every line
+carries `du_checksum` (sum of the bit patterns of du mod 2^64: bit-identical du for every N gives the same value).
 
-`--impl reference` times the CPU restatement of Trixi.jl's rhs! (oracle/, C++/OpenMP, all host threads) on a
-bounded sample of the same workload: Julia/Trixi.jl cannot run in this image, so the oracle port is
-the reference arm ("kind": "port").
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl reference] [--config C] [--level L]
+
+`--impl reference` times the CPU restatement of Trixi.jl's rhs! (oracle/, C++/OpenMP, every core of the affinity mask
+whatever OMP_NUM_THREADS says) on the SAME config and level when host memory allows: Julia/Trixi.jl cannot run in this
+image, so the oracle port is the reference arm ("kind": "port").
 """
 import argparse
 import json
@@ -25,8 +30,28 @@ import time
 ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
 
-BYTES_PER_DOF = 81.0   # 5 vars x 8 B read of u + 5 x 8 B write of du + ~1 B connectivity/Jacobian
-FLOP_PER_DOF = 420.0   # algorithmic FP64 flop per DOF-update, SURVEY.md section 8(d)
+# Algorithmic bytes per DOF-update: 8 nv read of u + 8 nv write of du + ~1 B connectivity / Jacobian; shock capturing
+# reads u twice (indicator pass + volume pass; the smoothed alpha is a global dependency) -- SURVEY.md section 8(d).
+# Algorithmic FP64 flop per DOF-update: counted by the oracle's instrumented scalar (oracle/opcount.py ->
+# profiles/r2_opcount.json; add = mul = div = sqrt = log = 1, fma = 2), hand estimate until that file exists.
+CONFIGS = {
+    1: dict(name="1D linear advection weak form LLF polydeg 3 TreeMesh level 4 (BASELINE.json configs[0])",
+            ndim=1, level=4, nvars=1, bytes_per_dof=17.0, flop_per_dof=15.0, key="c1_advection_1d"),
+    2: dict(name="2D compressible Euler EC flux differencing (flux_ranocha) polydeg 3 TreeMesh level 6 "
+                 "(BASELINE.json configs[1])",
+            ndim=2, level=6, nvars=4, bytes_per_dof=65.0, flop_per_dof=260.0, key="c2_euler_ec_2d"),
+    3: dict(name="3D compressible Euler shock capturing (Hennemann-Gassner blend, flux_ranocha) polydeg 3 TreeMesh "
+                 "level 5 (BASELINE.json configs[2])",
+            ndim=3, level=5, nvars=5, bytes_per_dof=121.0, flop_per_dof=480.0, key="c3_euler_sc_3d"),
+    4: dict(name="3D ideal GLM-MHD Alfven wave with non-conforming mortars polydeg 3, level 2 + box patch "
+                 "(BASELINE.json configs[3])",
+            ndim=3, level=2, nvars=9, bytes_per_dof=145.0, flop_per_dof=1100.0, key="c4_mhd_alfven_mortar_3d"),
+    5: dict(name="3D compressible Euler EC flux differencing (flux_ranocha volume+surface) polydeg 3 TreeMesh level 7 "
+                 "periodic [-2,2]^3, weak blast wave IC (BASELINE.json configs[4])",
+            ndim=3, level=7, nvars=5, bytes_per_dof=81.0, flop_per_dof=420.0, key="c5_euler_ec_3d"),
+}
+BOX3 = (dict(type="box", coordinates_min=(-0.5, -0.5, -0.5), coordinates_max=(0.5, 0.5, 0.5)),)
+PARITY_TOL = 1e-12          # BASELINE.json: du within 1e-12 relative (max-norm) after one rhs!
 
 
 def parse():
@@ -35,12 +60,28 @@ def parse():
     ap.add_argument("--steps", type=int, default=50)
     ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    ap.add_argument("--level", type=int, default=int(os.environ.get("TRIXIB200_BENCH_LEVEL", "7")))
+    ap.add_argument("--config", type=int, default=int(os.environ.get("TRIXIB200_BENCH_CONFIG", "5")),
+                    choices=sorted(CONFIGS))
+    ap.add_argument("--level", type=int, default=int(os.environ.get("TRIXIB200_BENCH_LEVEL", "0")),
+                    help="0: the level BASELINE.json names for the config")
+    ap.add_argument("--weak", action="store_true", help="config 5: level 7 per GPU (level 8 on 8 GPUs)")
     ap.add_argument("--e2e-steps", type=int, default=0, help="0: min(steps, 8)")
-    ap.add_argument("--cpu-level", type=int, default=5, help="mesh level of the bounded CPU sample")
+    ap.add_argument("--cpu-level", type=int, default=0, help="0: same level if host memory allows, else one below")
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
     ap.add_argument("--no-e2e", action="store_true")
-    return ap.parse_args()
+    ap.add_argument("--no-parity", action="store_true")
+    a = ap.parse_args()
+    if a.level == 0:
+        a.level = CONFIGS[a.config]["level"]
+    return a
+
+
+def flop_per_dof(config):
+    try:
+        oc = json.load(open(os.path.join(ROOT, "profiles", "r2_opcount.json")))
+        return float(oc[CONFIGS[config]["key"]]["flop_per_dof"]), "oracle OpCount<double> (profiles/r2_opcount.json)"
+    except Exception:
+        return CONFIGS[config]["flop_per_dof"], "hand estimate (SURVEY.md section 8(d))"
 
 
 # ------------------------------------------------------------------------------------------- clocks
@@ -99,77 +140,223 @@ class ClockSampler:
                 "samples": len(s)}
 
 
-# ------------------------------------------------------------------------------------------- CPU arm
-def cpu_sample(level, budget_s=12.0, threads=None):
-    """Times the oracle's rhs! (C++/OpenMP restatement of Trixi.jl's CPU rhs!) on the level-`level` version of the
-    workload with all host threads. Returns (dof_updates_per_s, cores, sample description, ms_per_rhs)."""
+# ------------------------------------------------------------------------------------------- CPU arm (oracle port)
+def host_cores():
+    """Cores this process may run on. torch.distributed.run exports OMP_NUM_THREADS=1, which omp_get_max_threads obeys;
+    the reference arm must use the box's cores, so the count comes from the affinity mask."""
+    try:
+        return max(1, len(os.sched_getaffinity(0)))
+    except Exception:
+        return max(1, os.cpu_count() or 1)
+
+
+def host_mem_available_gb():
+    try:
+        for ln in open("/proc/meminfo"):
+            if ln.startswith("MemAvailable:"):
+                return int(ln.split()[1]) / 1e6
+    except Exception:
+        pass
+    return 0.0
+
+
+def make_oracle(config, level):
     sys.path.insert(0, os.path.join(ROOT, "oracle"))
     import oracle as O
-    cores = O.max_threads() if threads is None else threads
+    if config == 1:
+        return O.Oracle(ndim=1, equations="advection", polydeg=3, advection_velocity=(1.0, 0.0, 0.0),
+                        initial_refinement_level=level)
+    if config == 2:
+        return O.Oracle(ndim=2, equations="euler", polydeg=3, volume_integral="flux_differencing",
+                        volume_flux="flux_ranocha", surface_flux="flux_ranocha", initial_condition="weak_blast_wave",
+                        coordinates_min=(-2.0,) * 3, coordinates_max=(2.0,) * 3, initial_refinement_level=level)
+    if config == 3:
+        return O.Oracle(ndim=3, equations="euler", polydeg=3, volume_integral="shock_capturing_hg",
+                        volume_flux="flux_ranocha", volume_flux_fv="flux_ranocha", surface_flux="flux_ranocha",
+                        initial_condition="weak_blast_wave", alpha_max=0.5, alpha_min=0.001, alpha_smooth=True,
+                        indicator_variable="density_pressure", coordinates_min=(-2.0,) * 3,
+                        coordinates_max=(2.0,) * 3, initial_refinement_level=level)
+    if config == 4:
+        return O.Oracle(ndim=3, equations="mhd", polydeg=3, volume_integral="flux_differencing",
+                        volume_flux="flux_hindenlang_gassner", surface_flux="flux_hlle", nonconservative=True,
+                        gamma=5 / 3, c_h=1.3, initial_refinement_level=level,
+                        refinement_patches=[(p["coordinates_min"], p["coordinates_max"]) for p in BOX3])
+    return O.Oracle(ndim=3, equations="euler", polydeg=3, volume_integral="flux_differencing",
+                    volume_flux="flux_ranocha", surface_flux="flux_ranocha", initial_condition="weak_blast_wave",
+                    gamma=1.4, coordinates_min=(-2.0,) * 3, coordinates_max=(2.0,) * 3,
+                    initial_refinement_level=level, periodicity=(True,) * 3)
+
+
+def cpu_level_for(args):
+    """The CPU arm runs the bench's own level when the oracle's Trixi-layout containers fit the host (level 7 of
+    config 5 needs ~32 GB), else one level below, and says which."""
+    if args.cpu_level:
+        return args.cpu_level
+    if args.config == 5 and args.level >= 7:
+        need_gb = 32.0 * 8 ** (args.level - 7)
+        return args.level if host_mem_available_gb() >= 1.5 * need_gb else (
+            args.level - 1 if host_mem_available_gb() >= 1.5 * need_gb / 8 else args.level - 2)
+    return args.level
+
+
+def checksum_np(a):
+    import numpy as np
+    return int(np.ascontiguousarray(a).view(np.uint64).sum(dtype=np.uint64))
+
+
+def time_oracle(o, u, warm, reps):
+    """Per-call wall times (seconds) of the oracle's rhs! after `warm` untimed calls (protocol of the reference's
+    benchmark/euler_ec_3d.jl:56-72: warm-up, then samples; median and mean reported)."""
+    if warm > 0:
+        o.time_rhs(u, warm=warm - 1, reps=1)
+    return [o.time_rhs(u, warm=0, reps=1) for _ in range(reps)]
+
+
+def cpu_sample(args, budget_s=20.0):
+    """cpu_baseline leg of the GPU arm: a bounded sample (~budget_s of CPU work) of the same workload."""
+    import numpy as np
+    sys.path.insert(0, os.path.join(ROOT, "oracle"))
+    import oracle as O
+    cores = host_cores()
     O.set_threads(cores)
-    o = O.Oracle(ndim=3, equations="euler", polydeg=3, volume_integral="flux_differencing",
-                 volume_flux="flux_ranocha", surface_flux="flux_ranocha", initial_condition="weak_blast_wave",
-                 gamma=1.4, coordinates_min=(-2.0,) * 3, coordinates_max=(2.0,) * 3, initial_refinement_level=level,
-                 periodicity=(True,) * 3)
+    level = args.cpu_level or (min(args.level, 6) if args.config == 5 else args.level)
+    o = make_oracle(args.config, level)
     u = o.compute_coefficients(0.0)
-    ndofs = o.nelements * 64
-    t1 = o.time_rhs(u, warm=1, reps=1)           # seconds for one rhs!
-    reps = int(max(3, min(200, budget_s / max(t1, 1e-6))))
-    t = o.time_rhs(u, warm=1, reps=reps) / reps  # mean seconds per rhs!
-    # the same sample on ONE thread (SURVEY.md section 8(d): report both), a few calls only
+    ndofs = o.nelements * o.nnodes ** o.ndim
+    t1 = o.time_rhs(u, warm=1, reps=1)
+    reps = int(max(5, min(200, budget_s / max(t1, 1e-6))))
+    ts = time_oracle(o, u, 0, reps)
+    med, mean = float(np.median(ts)), float(np.mean(ts))
     O.set_threads(1)
-    r1 = int(max(2, min(10, 3.0 / max(t * cores, 1e-6))))
-    t_one = o.time_rhs(u, warm=1, reps=r1) / r1
+    r1 = int(max(2, min(10, 4.0 / max(med * cores, 1e-6))))
+    t_one = float(np.median(time_oracle(o, u, 1, r1)))
     O.set_threads(cores)
-    return ndofs / t, cores, (f"3D Euler EC p=3 TreeMesh level {level} ({o.nelements} elements, {ndofs} DOF/field), "
-                              f"{reps} rhs! calls after 1 warm-up, {cores} OpenMP threads"), t * 1e3, reps, ndofs / t_one
+    sample = (f"config {args.config} at TreeMesh level {level} ({o.nelements} elements, {ndofs} DOF/field), median of "
+              f"{reps} rhs! calls after 2 warm-ups, {cores} OpenMP threads (Trixi-algorithm C++ restatement, Julia "
+              f"threads: n/a)")
+    return {"value": ndofs / med, "unit": "DOF-updates/s", "cores": cores, "kind": "port", "sample": sample,
+            "ms_per_rhs_median": med * 1e3, "ms_per_rhs_mean": mean * 1e3, "value_1_thread": ndofs / t_one,
+            "level": level}
 
 
 def run_reference(args):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return 0
-    K, W = max(args.steps, 1), args.warmup
+    import numpy as np
+    K, W = max(args.steps, 1), max(args.warmup, 1)
     sys.path.insert(0, os.path.join(ROOT, "oracle"))
     import oracle as O
-    cores = O.max_threads()
+    cores = host_cores()
     O.set_threads(cores)
-    level = args.cpu_level
-    o = O.Oracle(ndim=3, equations="euler", polydeg=3, volume_integral="flux_differencing",
-                 volume_flux="flux_ranocha", surface_flux="flux_ranocha", initial_condition="weak_blast_wave",
-                 gamma=1.4, coordinates_min=(-2.0,) * 3, coordinates_max=(2.0,) * 3, initial_refinement_level=level,
-                 periodicity=(True,) * 3)
+    level = cpu_level_for(args)
+    t0 = time.time()
+    o = make_oracle(args.config, level)
     u = o.compute_coefficients(0.0)
-    ndofs = o.nelements * 64
-    t = o.time_rhs(u, warm=max(W, 1), reps=K) / K    # mean seconds per rhs!
-    val = ndofs / t
-    sample = (f"each step = one rhs! on the level-{level} sample of the workload ({o.nelements} elements, {ndofs} "
-              f"DOF/field); DOF-updates/s is size-independent on the CPU once out of cache")
-    line = {"impl": "reference", "metric": "rhs! DOF-updates/s (1/PID) 3D Euler EC p=3", "value": val,
-            "unit": "DOF-updates/s", "n_gpus": args.gpus, "steps": K, "warmup": W, "ms_per_step": t * 1e3,
-            "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-            "config": {"workload": f"3D compressible Euler EC flux differencing (flux_ranocha) polydeg 3 TreeMesh "
-                                   f"level {args.level} periodic, weak blast wave IC", "cpu_sample_level": level},
+    setup_s = time.time() - t0
+    ndofs = o.nelements * o.nnodes ** o.ndim
+    # bounded: never more than ~4 minutes of timed calls whatever K says (each step is one rhs! of the sample)
+    t1 = o.time_rhs(u, warm=1, reps=1)
+    K_eff = int(max(3, min(K, 240.0 / max(t1, 1e-9))))
+    ts = time_oracle(o, u, max(W - 2, 0), K_eff)
+    med, mean = float(np.median(ts)), float(np.mean(ts))
+    val = ndofs / med
+    du = o.rhs(u, 0.0)
+    same = (level == args.level)
+    sample = (f"each step = one rhs! of config {args.config} at TreeMesh level {level} ({o.nelements} elements, {ndofs} "
+              f"DOF/field), {cores} OpenMP threads, median of {K_eff} calls"
+              + ("" if same else f"; the bench's level {args.level} does not fit this host's memory "
+                                 f"({host_mem_available_gb():.0f} GB available): DOF-updates/s is size-independent on "
+                                 f"the CPU once out of cache"))
+    line = {"impl": "reference", "metric": "rhs! DOF-updates/s (1/PID) " + metric_tail(args.config), "value": val,
+            "unit": "DOF-updates/s", "n_gpus": args.gpus, "steps": K_eff, "warmup": W, "ms_per_step": med * 1e3,
+            "ms_per_step_mean": mean * 1e3, "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
+            "dtype": "f64", "data": "synthetic",
+            "config": {"workload": CONFIGS[args.config]["name"] + f"; CPU arm at level {level} on {cores} cores",
+                       "level": level, "same_level_as_gpu_arm": same, "cores": cores, "setup_s": round(setup_s, 1)},
             "cpu_baseline": {"value": val, "unit": "DOF-updates/s", "cores": cores, "kind": "port", "sample": sample},
             "e2e": {"value": val, "unit": "DOF-updates/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
-            "gpu_launches": 0,
+            "gpu_launches": 0, "du_checksum_oracle": f"{checksum_np(du):016x}",
             "note": "Trixi.jl (Julia) cannot run in this image; this is the C++/OpenMP restatement of its CPU rhs!"}
     print(json.dumps(line), flush=True)
     return 0
 
 
+def metric_tail(config):
+    return {1: "1D advection p=3", 2: "2D Euler EC p=3", 3: "3D Euler SC p=3", 4: "3D GLM-MHD mortar p=3",
+            5: "3D Euler EC p=3"}[config]
+
+
 # ------------------------------------------------------------------------------------------- our arm
-def build_semi(level, rank, nranks, comm_id, device):
+def build_semi(config, level, rank, nranks, comm_id, device):
     import trixib200 as T
-    eq = T.CompressibleEulerEquations3D(1.4)
     basis = T.LobattoLegendreBasisGPU(3)
+    kw = dict(device=device, rank=rank, nranks=nranks, comm_id=comm_id)
+    if config == 1:
+        eq = T.LinearScalarAdvectionEquation1D((1.0,))
+        solver = T.DGSEMGPU(polydeg=3, surface_flux=T.flux_lax_friedrichs, basis=basis)
+        mesh = T.TreeMesh((-1.0,), (1.0,), initial_refinement_level=level, n_cells_max=10 ** 8)
+        return T.SemidiscretizationHyperbolicGPU(mesh, eq, T.initial_condition_convergence_test, solver, **kw)
+    if config == 2:
+        eq = T.CompressibleEulerEquations2D(1.4)
+        solver = T.DGSEMGPU(polydeg=3, surface_flux=T.flux_ranocha, basis=basis,
+                            volume_integral=T.VolumeIntegralFluxDifferencing(T.flux_ranocha))
+        mesh = T.TreeMesh((-2.0, -2.0), (2.0, 2.0), initial_refinement_level=level, n_cells_max=10 ** 8)
+        return T.SemidiscretizationHyperbolicGPU(mesh, eq, T.initial_condition_weak_blast_wave, solver, **kw)
+    if config == 3:
+        eq = T.CompressibleEulerEquations3D(1.4)
+        ind = T.IndicatorHennemannGassner(eq, basis, alpha_max=0.5, alpha_min=0.001, alpha_smooth=True,
+                                          variable=T.density_pressure)
+        vi = T.VolumeIntegralShockCapturingHG(ind, volume_flux_dg=T.flux_ranocha, volume_flux_fv=T.flux_ranocha)
+        solver = T.DGSEMGPU(polydeg=3, surface_flux=T.flux_ranocha, volume_integral=vi, basis=basis)
+        mesh = T.TreeMesh((-2.0,) * 3, (2.0,) * 3, initial_refinement_level=level, n_cells_max=10 ** 8)
+        return T.SemidiscretizationHyperbolicGPU(mesh, eq, T.initial_condition_weak_blast_wave, solver,
+                                                 node_coordinates=False, **kw)
+    if config == 4:
+        eq = T.IdealGlmMhdEquations3D(5 / 3, initial_c_h=1.3)
+        vf = (T.flux_hindenlang_gassner, T.flux_nonconservative_powell)
+        sf = (T.flux_hlle, T.flux_nonconservative_powell)
+        solver = T.DGSEMGPU(polydeg=3, surface_flux=sf, volume_integral=T.VolumeIntegralFluxDifferencing(vf),
+                            basis=basis)
+        mesh = T.TreeMesh((-1.0,) * 3, (1.0,) * 3, initial_refinement_level=level, refinement_patches=BOX3,
+                          n_cells_max=10 ** 8)
+        return T.SemidiscretizationHyperbolicGPU(mesh, eq, T.initial_condition_convergence_test, solver, **kw)
+    eq = T.CompressibleEulerEquations3D(1.4)
     vi = T.VolumeIntegralFluxDifferencing(T.flux_ranocha)
     solver = T.DGSEMGPU(polydeg=3, surface_flux=T.flux_ranocha, volume_integral=vi, basis=basis)
     mesh = T.TreeMesh((-2.0, -2.0, -2.0), (2.0, 2.0, 2.0), initial_refinement_level=level, periodicity=True,
-                      n_cells_max=10 ** 8)
+                      n_cells_max=10 ** 9)
     return T.SemidiscretizationHyperbolicGPU(mesh, eq, T.initial_condition_weak_blast_wave, solver,
-                                             device=device, rank=rank, nranks=nranks, comm_id=comm_id,
-                                             node_coordinates=False)
+                                             node_coordinates=False, **kw)
+
+
+def parity_check(args, rank, world, comm_id, local_rank, dist, dev):
+    """du of the product against the CPU oracle on the same mesh, equations and IC before anything is timed: config 5 at
+    level 5 (the oracle needs 33 ms there), configs 1-4 at their full size; N > 1: every rank checks its Morton range."""
+    import numpy as np
+    import torch
+    level = min(args.level, 5) if args.config == 5 else args.level
+    o = make_oracle(args.config, level)
+    u = o.compute_coefficients(0.0)
+    ref = o.rhs(u, 0.0)
+    semi = build_semi(args.config, level, rank, world, comm_id, local_rank)
+    per = semi.nvars * semi.nnodes ** semi.mesh.ndim
+    lo, hi = per * semi.first_element, per * (semi.first_element + semi.nelements)
+    ud = torch.from_numpy(np.ascontiguousarray(u[lo:hi])).to(dev)
+    du = semi.new_vector()
+    semi.rhs(du, ud, 0.0)
+    torch.cuda.synchronize()
+    err = float(np.abs(du.cpu().numpy() - ref[lo:hi]).max() / np.abs(ref).max())
+    if dist is not None:
+        t = torch.tensor([err], dtype=torch.float64, device=dev)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        err = float(t.item())
+    del semi, du, ud
+    torch.cuda.empty_cache()
+    if not err <= PARITY_TOL:
+        raise SystemExit(f"bench.py: du differs from the CPU oracle at level {level}: rel max err {err:.3e} > {PARITY_TOL}")
+    return {"against": "oracle (CPU restatement of Trixi.jl's rhs!)", "level": level, "rel_max_err": err,
+            "tolerance": PARITY_TOL, "metric": "max|du - du_ref| / max|du_ref|", "ranks": world}
 
 
 def run_ours(args):
@@ -184,9 +371,19 @@ def run_ours(args):
     dev = torch.device("cuda", local_rank)
     comm_id = D.broadcast_comm_id() if world > 1 else None
     K, W = max(args.steps, 1), max(args.warmup, 3)
+    cfg = CONFIGS[args.config]
+    level = args.level
+    if args.weak and args.config == 5:
+        level = args.level + {1: 0, 2: 0, 4: 0, 8: 1}.get(world, 0)      # 8 ranks: level 8, each rank a level-7 octant
+    resident = args.config == 5           # working set >> L2; the small configs flush L2 between timed calls
+
+    parity = None
+    if not args.no_parity:
+        pc_id = D.broadcast_comm_id() if world > 1 else None
+        parity = parity_check(args, rank, world, pc_id, local_rank, dist, dev)
 
     t0 = time.time()
-    semi = build_semi(args.level, rank, world, comm_id, local_rank)
+    semi = build_semi(args.config, level, rank, world, comm_id, local_rank)
     setup_s = time.time() - t0
     ndofs_global, ndofs_local = semi.ndofsglobal(), semi.ndofs()
     u = semi.compute_coefficients_gpu(0.0, on_device=True)
@@ -212,47 +409,72 @@ def run_ours(args):
     clocks = ClockSampler(local_rank)
     clocks.start()
     l0 = semi.launch_count()
-    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    e0.record()
-    for _ in range(K):
-        T.rhs_gpu_(du, u, semi, 0.0)
-    e1.record()
-    barrier()
-    ms_total = max_over_ranks(e0.elapsed_time(e1))
+    per_call = None
+    if resident:
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(K):
+            T.rhs_gpu_(du, u, semi, 0.0)
+        e1.record()
+        barrier()
+        ms_total = max_over_ranks(e0.elapsed_time(e1))
+    else:
+        flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)      # 2x the 126 MB L2
+        evs = []
+        for _ in range(K):
+            flush.fill_(1)
+            a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            a.record()
+            T.rhs_gpu_(du, u, semi, 0.0)
+            b.record()
+            evs.append((a, b))
+        barrier()
+        per_call = sorted(a.elapsed_time(b) for a, b in evs)
+        ms_total = max_over_ranks(sum(per_call))
+        del flush
     launches = semi.launch_count() - l0
     ms_step = ms_total / K
     value = ndofs_global / (ms_step * 1e-3)
     if not bool(torch.isfinite(du).all().item()):
         raise SystemExit("bench.py: non-finite du")
+    cks = du.view(torch.int64).sum()          # wraps mod 2^64: order-independent, exact
+    if dist is not None:
+        dist.all_reduce(cks, op=dist.ReduceOp.SUM)
+    du_checksum = f"{int(cks.item()) & 0xFFFFFFFFFFFFFFFF:016x}"
 
     # ---- context: one CarpenterKennedy2N54 stage, rhs! + update kernel vs the fused trixib200_rk2n_stage
     extras = {}
-    try:
-        u2, tmp = semi.new_vector(), semi.new_vector().zero_()
-        a, b, dt = -0.4178904745, 0.3792103129999, 1e-4
+    if args.config == 5:
+        try:
+            u2, tmp = semi.new_vector(), semi.new_vector().zero_()
+            a, b, dt = -0.4178904745, 0.3792103129999, 1e-4
 
-        def timed(fn, reps=min(K, 10)):
-            for _ in range(2):
-                fn()
-            barrier()
-            f0, f1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-            f0.record()
-            for _ in range(reps):
-                fn()
-            f1.record()
-            barrier()
-            return max_over_ranks(f0.elapsed_time(f1)) / reps
+            def timed(fn, reps=min(K, 10)):
+                for _ in range(2):
+                    fn()
+                barrier()
+                f0, f1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                f0.record()
+                for _ in range(reps):
+                    fn()
+                f1.record()
+                barrier()
+                return max_over_ranks(f0.elapsed_time(f1)) / reps
 
-        def unfused():
+            def unfused():
+                T.rhs_gpu_(du, u, semi, 0.0)
+                semi.rk2n_update(u2, tmp, du, a, b, dt)
+
+            extras = {"rk2n_stage_unfused_ms": timed(unfused),
+                      "rk2n_stage_fused_ms": timed(lambda: semi.rk2n_stage(u2, u, tmp, 0.0, a, b, dt)),
+                      "note": "one 2N Runge-Kutta stage at the same size: rhs! + update kernel vs trixib200_rk2n_stage"}
+            del u2, tmp
             T.rhs_gpu_(du, u, semi, 0.0)
-            semi.rk2n_update(u2, tmp, du, a, b, dt)
-
-        extras = {"rk2n_stage_unfused_ms": timed(unfused),
-                  "rk2n_stage_fused_ms": timed(lambda: semi.rk2n_stage(u2, u, tmp, 0.0, a, b, dt)),
-                  "note": "one 2N Runge-Kutta stage at the same size: rhs! + update kernel vs trixib200_rk2n_stage"}
-        del u2, tmp
-    except Exception as ex:  # context only: never fail the bench line over it
-        extras = {"error": repr(ex)}
+        except Exception as ex:  # context only: never fail the bench line over it
+            extras = {"error": repr(ex)}
+    if per_call:
+        extras["us_per_rhs_median"] = per_call[len(per_call) // 2] * 1e3
+        extras["us_per_rhs_min"] = per_call[0] * 1e3
 
     # ---- end to end: host vectors in, host vectors out, every step
     e2e = None
@@ -271,8 +493,9 @@ def run_ours(args):
         barrier()
         sec = max_over_ranks(time.perf_counter() - t0)
         ok = bool(torch.equal(du_host, du.cpu()))
+        nglob = ndofs_global * semi.nvars
         e2e = {"value": ndofs_global * Ke / sec, "unit": "DOF-updates/s",
-               "h2d_bytes_per_step": int(nloc * 8 * world), "d2h_bytes_per_step": int(nloc * 8 * world),
+               "h2d_bytes_per_step": int(nglob * 8), "d2h_bytes_per_step": int(nglob * 8),
                "steps": Ke, "ms_per_step": sec / Ke * 1e3, "matches_device_path": ok,
                "api": "SemidiscretizationHyperbolicGPU.rhs_host -> trixib200_rhs_host (pinned host u, du)"}
         del u_host, du_host
@@ -280,19 +503,24 @@ def run_ours(args):
 
     if rank != 0:
         return 0
-    # ---- roofline of the dominant kernel (at N=1 the rhs! IS one launch of k_line6)
-    peaks, peak_src = {}, "fallback"
+    # ---- roofline of the dominant kernel
+    peaks, peak_src = {}, "fallback 6650 GB/s (B200_PROFILING.md)"
     try:
         peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
-        peak_src = "measured"
+        peak_src = "measured (MEASURED_PEAKS.json hbm_gbs)"
     except Exception:
         pass
     hbm_peak = float(peaks.get("hbm_gbs", 6650.0))
-    achieved = BYTES_PER_DOF * ndofs_local / (ms_step * 1e-3) / 1e9
-    traffic = None
+    bpd = cfg["bytes_per_dof"]
+    achieved = bpd * ndofs_local / (ms_step * 1e-3) / 1e9
+    traffic, traffic_src = None, None
     try:
-        traffic = json.load(open(os.path.join(ROOT, "profiles", "traffic.json"))).get("k_line6_bytes_per_dof")
-        traffic = traffic * ndofs_local if traffic is not None else None
+        tj = json.load(open(os.path.join(ROOT, "profiles", "traffic.json")))
+        key = {5: "k_line6_bytes_per_dof", 3: "k_fused_sc_bytes_per_dof"}.get(args.config)
+        if key and tj.get(key) is not None:
+            traffic = tj[key] * ndofs_local
+            traffic_src = tj.get("source", "ncu --set full capture under profiles/ (dram__bytes_read+write per DOF), "
+                                           "scaled to this launch; not re-measured in this run")
     except Exception:
         pass
     fp64_peak = None
@@ -300,35 +528,45 @@ def run_ours(args):
         fp64_peak = json.load(open(os.path.join(ROOT, "profiles", "fp64_peak.json"))).get("fp64_tflops")
     except Exception:
         pass
+    fpd, fpd_src = flop_per_dof(args.config)
+    kernel = {1: "k_volume + staged kernels (1D weak form)", 2: "k_fused<EqEuler<2>, flux differencing>",
+              3: "k_indicator + k_alpha_smooth + k_fused<EqEuler<3>, shock capturing>",
+              4: "staged mortar kernels + k_fused<EqMhd, flux differencing + Powell>"}.get(args.config)
+    if args.config == 5:
+        kernel = semi_kernel_name(semi)
+    tf = fpd * ndofs_local / (ms_step * 1e-3) / 1e12
     roofline = {"bound": "hbm", "achieved": achieved, "peak": hbm_peak, "unit": "GB/s", "frac": achieved / hbm_peak,
-                "traffic": traffic, "peak_source": peak_src + " (MEASURED_PEAKS.json hbm_gbs)",
-                "kernel": ("k_line6<flux_ranocha, flux_ranocha, SFV=0, 4 warps, 2 CTAs/SM, 8 pairs staged>" if semi.line3d else
-                           "k_warp3d<EqEuler<3>, flux_ranocha, flux_ranocha>" if semi.warp3d else "k_fused"),
-                "algorithmic_bytes_per_dof": BYTES_PER_DOF,
-                "fp64": {"algorithmic_flop_per_dof": FLOP_PER_DOF,
-                         "achieved_tflops": FLOP_PER_DOF * ndofs_local / (ms_step * 1e-3) / 1e12,
-                         "peak_tflops_measured_dfma": fp64_peak,
-                         "frac": (FLOP_PER_DOF * ndofs_local / (ms_step * 1e-3) / 1e12 / fp64_peak) if fp64_peak else None,
-                         "note": "issue-bound: time = sum of the issue costs of ~1350 FP64 (2 cycles) and ~1300 other "
-                                 "instructions per element pair and scheduler (profiles/r1_line6_notes.md)"}}
-    line = {"metric": "rhs! DOF-updates/s (1/PID) 3D Euler EC p=3", "value": value, "unit": "DOF-updates/s",
-            "n_gpus": world, "steps": K, "warmup": W, "ms_per_step": ms_step, "higher_is_better": True,
-            "scaling": "strong", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-            "config": {"workload": f"3D compressible Euler EC flux differencing (flux_ranocha volume+surface) polydeg 3 "
-                                   f"TreeMesh level {args.level} periodic [-2,2]^3, weak blast wave IC "
-                                   f"(BASELINE.json configs[4])",
-                       "nelements": semi.nelements_global, "ndofs_per_field": ndofs_global, "nvars": 5,
-                       "partition": f"morton{world}", "l2_policy": "inputs larger than L2 "
-                       f"(u+du = {2 * 40 * ndofs_local / 1e9:.2f} GB per rank vs 126 MB L2), no flush",
+                "traffic": traffic, "traffic_source": traffic_src, "peak_source": peak_src, "kernel": kernel,
+                "algorithmic_bytes_per_dof": bpd,
+                "fp64": {"algorithmic_flop_per_dof": fpd, "flop_count_source": fpd_src, "achieved_tflops": tf,
+                         "peak_tflops_measured_dfma": fp64_peak, "frac": (tf / fp64_peak) if fp64_peak else None}}
+    if not resident:
+        roofline["note"] = ("L2-resident / launch-latency-bound configuration: absolute us per rhs! is the figure of "
+                            "merit (SURVEY.md section 8(d)); L2 flushed between timed calls")
+    line = {"metric": "rhs! DOF-updates/s (1/PID) " + metric_tail(args.config), "value": value,
+            "unit": "DOF-updates/s", "n_gpus": world, "steps": K, "warmup": W, "ms_per_step": ms_step,
+            "higher_is_better": True, "scaling": "weak" if (args.weak and args.config == 5) else "strong",
+            "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+            "config": {"workload": cfg["name"] + (f" [run at level {level}]" if level != cfg["level"] else ""),
+                       "level": level, "nelements": semi.nelements_global, "ndofs_per_field": ndofs_global,
+                       "nvars": semi.nvars, "partition": f"morton{world}",
+                       "l2_policy": (f"inputs larger than L2 (u+du = {2 * 8 * semi.nvars * ndofs_local / 1e9:.2f} GB per "
+                                     f"rank vs 126 MB L2), no flush") if resident else
+                                    "L2 flushed (256 MB write) before every timed call; calls timed one by one",
                        "setup_s": round(setup_s, 1)},
             "roofline": roofline, "e2e": e2e, "gpu_launches": int(launches), "clocks": clocks.summary(),
-            "extras": extras}
+            "du_checksum": du_checksum, "parity": parity, "extras": extras}
     if world == 1 and not args.no_cpu:
-        v, cores, sample, ms, reps, v_one = cpu_sample(args.cpu_level)
-        line["cpu_baseline"] = {"value": v, "unit": "DOF-updates/s", "cores": cores, "kind": "port",
-                                "sample": sample, "ms_per_rhs": ms, "value_1_thread": v_one}
+        line["cpu_baseline"] = cpu_sample(args)
     print(json.dumps(line), flush=True)
     return 0
+
+
+def semi_kernel_name(semi):
+    if semi.line3d:
+        return ("k_line6<flux_ranocha, flux_ranocha> (line-owner fused rhs!, shape "
+                + os.environ.get("TRIXIB200_LINE_SHAPE", "default") + ")")
+    return "k_warp3d" if semi.warp3d else "k_fused"
 
 
 def main():

@@ -51,9 +51,21 @@ constexpr unsigned L6_ROUGH_HI = 0x3F1A36E2u;
 // that consecutive instructions are independent. hw[k] = larger high word of the two squared relative jumps of pair k:
 // the pair needs the logarithmic branch iff hw[k] >= L6_ROUGH_HI (one integer max per pair on the hot path; the caller
 // reduces them to ONE comparison per batch).
-template <bool FAST, int K0, int NP>
+// SEEDS: the high words of the two reciprocal seeds of every pair were computed ahead (l6_seeds), the MUFU latency is
+// then outside this function.
+template <int NP> TB_D void l6_seeds(const double (&Q)[6][5], int (&seed_s)[NP], int (&seed_t)[NP]) {
+#pragma unroll
+  for (int k = 0; k < NP; ++k) {
+    const double* a = Q[L6_PA[k]]; const double* b = Q[L6_PB[k]];
+    double r, rt;
+    asm("rcp.approx.ftz.f64 %0, %1;" : "=d"(r) : "d"(a[0] + b[0]));
+    asm("rcp.approx.ftz.f64 %0, %1;" : "=d"(rt) : "d"(a[0] * b[4] + b[0] * a[4]));
+    seed_s[k] = __double2hiint(r); seed_t[k] = __double2hiint(rt);
+  }
+}
+template <bool FAST, int K0, int NP, bool SEEDS = false>
 TB_D void l6_fluxes(const double (&Q)[6][5], int vflux, int sflux, const EqPrm& prm, double (&F)[NP][5],
-                    unsigned (&hw)[NP]) {
+                    unsigned (&hw)[NP], const int* seed_s = nullptr, const int* seed_t = nullptr) {
   if (FAST) {
     double s[NP], r[NP], dd[NP], tt[NP], rt[NP], xy[NP], rm[NP], im[NP];
 #pragma unroll
@@ -64,8 +76,13 @@ TB_D void l6_fluxes(const double (&Q)[6][5], int vflux, int sflux, const EqPrm& 
       const double x = a[0] * b[4], y = b[0] * a[4];
       tt[k] = x + y;
       xy[k] = x - y;
-      asm("rcp.approx.ftz.f64 %0, %1;" : "=d"(r[k]) : "d"(s[k]));
-      asm("rcp.approx.ftz.f64 %0, %1;" : "=d"(rt[k]) : "d"(tt[k]));
+      if (SEEDS) {
+        r[k] = __hiloint2double(seed_s[K0 + k], 0);
+        rt[k] = __hiloint2double(seed_t[K0 + k], 0);
+      } else {
+        asm("rcp.approx.ftz.f64 %0, %1;" : "=d"(r[k]) : "d"(s[k]));
+        asm("rcp.approx.ftz.f64 %0, %1;" : "=d"(rt[k]) : "d"(tt[k]));
+      }
     }
 #pragma unroll
     for (int k = 0; k < NP; ++k) {
@@ -109,7 +126,32 @@ constexpr int l6_maxnreg(int warps, int ctas) {
   return r > 255 ? 255 : r;
 }
 
-template <int VFLUX, int SFLUX, bool SFV, int WARPS, int CTAS, int NP, bool RK = false, bool TOUT = false>
+// PP ("ping-pong"): one CTA of 3 warpgroups per SM (12 warps, launched at 168 registers). A phase is split into a
+// register-light part (gather q / traces / running sums from shared memory, hand-over, stores, cp.async issue: <= L6_PP_LO
+// registers) and the flux part (8 staged pair fluxes + accumulation: L6_PP_HI registers). Only ONE warpgroup is in its
+// flux part at a time: it takes the token (named barrier), grows to L6_PP_HI registers with setmaxnreg.inc -- the other
+// two warpgroups have shrunk to L6_PP_LO with setmaxnreg.dec -- and hands registers and token on when its 8 fluxes are
+// accumulated. Every SM sub-partition then holds one warp that feeds the FP64 pipe at its 2-cycle cadence and two warps
+// whose shared-memory / address / copy instructions issue in the gaps, instead of two warps that are in the same kind
+// of section half of the time (profiles/r1_line6_notes.md: 0.68 eligible warps per cycle, FP64 pipe 52 % busy).
+#ifndef L6_PP_HI
+#define L6_PP_HI 232
+#define L6_PP_LO 136     // 232 + 2 * 136 = 504 = 3 * 168
+#endif
+template <int REGS> TB_D void l6_reg_inc() { asm volatile("setmaxnreg.inc.sync.aligned.u32 %0;\n" ::"n"(REGS)); }
+template <int REGS> TB_D void l6_reg_dec() { asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;\n" ::"n"(REGS)); }
+TB_D void l6_bar_sync(int id, int n) { asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(n) : "memory"); }
+TB_D void l6_bar_arrive(int id, int n) { asm volatile("bar.arrive %0, %1;" ::"r"(id), "r"(n) : "memory"); }
+// the same, issued once `dep` has been computed (ptxas moves arithmetic across a volatile asm, a data dependence pins it)
+TB_D void l6_bar_arrive_after(int id, int n, double dep) {
+  asm volatile("bar.arrive %0, %1;" ::"r"(id), "r"(n), "d"(dep) : "memory");
+}
+#ifndef L6_PP_ARRIVE_K
+#define L6_PP_ARRIVE_K 5     // the token is passed on when pair K of the 8 has been accumulated (8: behind setmaxnreg.dec)
+#endif
+
+template <int VFLUX, int SFLUX, bool SFV, int WARPS, int CTAS, int NP, bool RK = false, bool TOUT = false,
+          bool PP = false>
 __global__ void __launch_bounds__(32 * WARPS) __maxnreg__(l6_maxnreg(WARPS, CTAS))
 k_line6(const __grid_constant__ Dev d, const __grid_constant__ LineOps ops, double* __restrict__ du,
         const double* __restrict__ u, double t, const int* __restrict__ elems, int64_t count,
@@ -131,12 +173,25 @@ k_line6(const __grid_constant__ Dev d, const __grid_constant__ LineOps ops, doub
   // (a self-shuffle: ptxas cannot see through it, an empty asm only stops the front end)
   lp = __shfl_sync(0xffffffffu, lp, threadIdx.x & 31);
   sb = __shfl_sync(0xffffffffu, sb, threadIdx.x & 31);
-  const int half = lp >> 4, l16 = lp & 15;
-  const int la = l16 & 3, lb = l16 >> 2;
-  double* ebase = reinterpret_cast<double*>(__cvta_shared_to_generic((size_t)sb));
-  double* sq = ebase;                    // AoS landing zone of the element block, then the swizzled SoA q [5][64]
-  double* sacc = ebase + L6_TILE;        // swizzled SoA running sums [5][64], handed from phase to phase
-  double* tr = ebase + 2 * L6_TILE;      // face traces of the six neighbours
+  // Everything derived from the lane id. PP re-derives it from the two opaque registers at the top of every phase and
+  // again behind the flux part: ptxas otherwise hoists ~25 lane-dependent addresses out of the persistent loop and, as
+  // the register-light parts have 136 registers, keeps them in LOCAL memory (one L2 round trip per reload: the first
+  // PP build spent 25 % of its stall samples on them, profiles/r2_line6_pingpong.md).
+  int half, l16, la, lb, Px, Py, Pz;
+  double *sq, *sacc, *tr;
+  auto relane = [&]() {
+    unsigned a = lp, b = sb;
+    if (PP) asm volatile("" : "+r"(a), "+r"(b));
+    half = a >> 4; l16 = a & 15;
+    la = l16 & 3; lb = l16 >> 2;
+    double* ebase = reinterpret_cast<double*>(__cvta_shared_to_generic((size_t)b));
+    sq = ebase;                    // AoS landing zone of the element block, then the swizzled SoA q [5][64]
+    sacc = ebase + L6_TILE;        // swizzled SoA running sums [5][64], handed from phase to phase
+    tr = ebase + 2 * L6_TILE;      // face traces of the six neighbours
+    // tile positions of this lane's line nodes: P ^ (m * stride) with stride 1 (x), 4 (y), 21 (z)
+    Px = 16 * lb + 4 * (la ^ lb) + lb; Py = 20 * lb + (la ^ lb); Pz = l16;
+  };
+  relane();
   const EqPrm prm = d.prm;
   const double gm1 = prm.gamma - 1;
   const int vflux = (VFLUX >= 0) ? VFLUX : d.vol_flux;
@@ -202,9 +257,15 @@ k_line6(const __grid_constant__ Dev d, const __grid_constant__ LineOps ops, doub
   using D1 = std::integral_constant<int, 1>;
   using D2 = std::integral_constant<int, 2>;
 
-  // tile positions of this lane's line nodes: P ^ (m * stride) with stride 1 (x), 4 (y), 21 (z)
-  const int Px = 16 * lb + 4 * (la ^ lb) + lb, Py = 20 * lb + (la ^ lb), Pz = l16;
-
+  static_assert(!PP || (WARPS == 12 && CTAS == 1 && NP >= 4), "ping-pong shape: 3 warpgroups, one CTA per SM");
+  // PP: every warp of the CTA runs the same number of iterations (the token goes round the three warpgroups in a fixed
+  // order); warps whose pair index runs past the end repeat the last element with their stores switched off
+  const int wg = (threadIdx.x >> 7);
+  const int niter = PP ? (npairs + nw - 1) / nw : 0;
+  if (PP) {
+    l6_reg_dec<L6_PP_LO>();
+    if (wg == 2) l6_bar_arrive(1, 256);       // the first token goes to warpgroup 0
+  }
   unsigned fbits = 0;
   int pr = wid;
   bool valid = false;
@@ -212,7 +273,7 @@ k_line6(const __grid_constant__ Dev d, const __grid_constant__ LineOps ops, doub
   // cp.async groups are committed in the order  z-traces, y-traces, block, x-traces  (of the NEXT pair): at the top
   // of an iteration only the x-traces may be pending (wait_group 1), at the x phase the z- and y-traces of the next
   // pair (wait_group 2)
-  if (pr < npairs) {
+  if (PP || pr < npairs) {
     e = elem_of(pr, valid);
     const int2 cx = load_codes(e, 0), cy = load_codes(e, 1), cz = load_codes(e, 2);
     fbits = face_bits(cx, 0) | face_bits(cy, 1) | face_bits(cz, 2);
@@ -222,12 +283,14 @@ k_line6(const __grid_constant__ Dev d, const __grid_constant__ LineOps ops, doub
     issue_traces(D0{}, e, cx.x, cx.y); cp_async_commit();
   }
 
-  for (; pr < npairs; pr += nw) {
-    const int pr_next = (pr + nw < npairs) ? pr + nw : pr;   // the last iteration prefetches its own element again
+  for (int it = 0; PP ? it < niter : pr < npairs; pr += nw, ++it) {
+    // the last iteration prefetches its own element again (PP: elem_of clamps a pair index past the end)
+    const int pr_next = (PP || pr + nw < npairs) ? pr + nw : pr;
     bool valid_next = false;
     const int e_next = elem_of(pr_next, valid_next);
     unsigned fbits_next = 0;
     const double inv_jac = d.inv_jac[e];
+    if (PP) relane();
 
     // ---- the block has landed: cons -> q in place. Lane (la, lb) reads the nodes (la, lb, m) = its z-line.
     cp_async_wait<1>();
@@ -257,14 +320,21 @@ k_line6(const __grid_constant__ Dev d, const __grid_constant__ LineOps ops, doub
 #pragma unroll 1
     for (int step = 0; step < 3; ++step) {
       const int dir = 2 - step;
+      if (PP) relane();
       // rows of the velocity / momentum components in slot order (slot 1 = normal component)
       const int c0 = 1 + dir, c1 = (dir == 2) ? 1 : dir + 2, c2 = (dir == 0) ? 3 : dir;
       const int r0 = c0 * NN, r1 = c1 * NN, r2 = c2 * NN;
       const int2 cn = load_codes(e_next, dir);   // issued early, consumed when the trace copies are issued
       const unsigned fb = fbits >> (4 * dir);
-      const int P = dir == 0 ? Px : (dir == 1 ? Py : Pz);
       const int stp = dir == 0 ? 1 : (dir == 1 ? 4 : 21);
-      const int pos[4] = {P, P ^ stp, P ^ (2 * stp), P ^ (3 * stp)};
+      int pos[4];
+      double2* xt;                   // TILE: this lane's row of the output tile (10 chunks, stride 11)
+      auto repos = [&]() {
+        const int P = dir == 0 ? Px : (dir == 1 ? Py : Pz);
+        pos[0] = P; pos[1] = P ^ stp; pos[2] = P ^ (2 * stp); pos[3] = P ^ (3 * stp);
+        xt = reinterpret_cast<double2*>(sacc) + 11 * l16;
+      };
+      repos();
       const int ec = e;
       const bool valid_c = valid;
       if (step == 2) {
@@ -346,19 +416,39 @@ k_line6(const __grid_constant__ Dev d, const __grid_constant__ LineOps ops, doub
           if (rk.a != 0.0) asm volatile("prefetch.global.L1 [%0];" ::"l"(bt + 128 * (16 + l16)));
         }
       }
-      double2* xt = reinterpret_cast<double2*>(sacc) + 11 * l16;   // TILE: this lane's row (10 chunks, stride 11)
 
       // ---- the 8 pair fluxes of the line in batches of NP (reference dg_3d_kernel.jl:188-257 evaluates 12 volume
       // fluxes per node, and the interface fluxes in two more kernels); a node is handed over as soon as its last pair
       // is in: node 0 after pair 3, node 1 after pair 5, nodes 2 and 3 after pair 7
       double acc[4][NV];
-      load_old(0, acc[0]);
+      int seed_s[8], seed_t[8];
+      if (PP) {
+        l3_to_q(nbv[1], gm1, Q[5]);    // all six virtual nodes are ready before the token is taken
+#ifdef L6_PP_SEED_EARLY
+        if (FAST) l6_seeds<8>(Q, seed_s, seed_t);
+#endif
+#ifdef L6_PP_ACC_EARLY
+        // the running sums too (40 more registers live across the wait)
+        load_old(0, acc[0]); load_old(1, acc[1]); load_old(2, acc[2]); load_old(3, acc[3]);
+#endif
+        l6_bar_sync(1 + wg, 256);      // token: this warpgroup's turn on the FP64 pipe
+        l6_reg_inc<L6_PP_HI>();
+#ifndef L6_PP_ACC_EARLY
+        load_old(0, acc[0]); load_old(1, acc[1]); load_old(2, acc[2]); load_old(3, acc[3]);
+#endif
+      } else {
+        load_old(0, acc[0]);
+      }
       auto batch = [&](auto k0_tag) {
         constexpr int K0 = decltype(k0_tag)::value;
-        if (K0 + NP > 7) l3_to_q(nbv[1], gm1, Q[5]);   // converted when its pair comes up
+        if (!PP && K0 + NP > 7) l3_to_q(nbv[1], gm1, Q[5]);   // converted when its pair comes up
         double F[NP][NV];
         unsigned hw[NP];
+#ifdef L6_PP_SEED_EARLY
+        l6_fluxes<FAST, K0, NP, PP && FAST>(Q, vflux, sflux, prm, F, hw, seed_s, seed_t);
+#else
         l6_fluxes<FAST, K0, NP>(Q, vflux, sflux, prm, F, hw);
+#endif
         if (SFV && K0 == 0) {
           if (sfv_lo) hw[0] = 0;      // the trace IS the flux: nothing to correct
 #pragma unroll
@@ -372,9 +462,11 @@ k_line6(const __grid_constant__ Dev d, const __grid_constant__ LineOps ops, doub
         unsigned worst = hw[0];
 #pragma unroll
         for (int k = 1; k < NP; ++k) worst = max(worst, hw[k]);
-        if (K0 <= 1 && K0 + NP > 1) load_old(1, acc[1]);
-        if (K0 <= 2 && K0 + NP > 2) load_old(2, acc[2]);
-        if (K0 <= 3 && K0 + NP > 3) load_old(3, acc[3]);
+        if (!PP) {
+          if (K0 <= 1 && K0 + NP > 1) load_old(1, acc[1]);
+          if (K0 <= 2 && K0 + NP > 2) load_old(2, acc[2]);
+          if (K0 <= 3 && K0 + NP > 3) load_old(3, acc[3]);
+        }
         auto accumulate = [&](int k, int v) {
           const int kk = K0 + k;
           if (kk == 0) acc[0][v] = fma(-ops.factor_1, F[k][v], acc[0][v]);
@@ -386,9 +478,14 @@ k_line6(const __grid_constant__ Dev d, const __grid_constant__ LineOps ops, doub
           }
         };
 #pragma unroll
-        for (int k = 0; k < NP; ++k)
+        for (int k = 0; k < NP; ++k) {
 #pragma unroll
           for (int v = 0; v < NV; ++v) accumulate(k, v);
+          // PP: the next warpgroup is woken a little before this one gives its registers back, so that its wake-up
+          // latency is hidden behind the last accumulations
+          if (PP && K0 + k == L6_PP_ARRIVE_K)
+            l6_bar_arrive_after(wg == 2 ? 1 : 2 + wg, 256, acc[L6_PB[K0 + k] - 1 > 3 ? 3 : L6_PB[K0 + k] - 1][NV - 1]);
+        }
         if (FAST && worst >= L6_ROUGH_HI) {
 #pragma unroll
           for (int k = 0; k < NP; ++k)
@@ -409,6 +506,14 @@ k_line6(const __grid_constant__ Dev d, const __grid_constant__ LineOps ops, doub
                 }
               }
             }
+        }
+        if (PP && K0 + NP > 7) {
+          // the 8 fluxes are accumulated: registers and token go to the next warpgroup (warpgroup 0
+          // absorbs the last one behind the loop)
+          if (L6_PP_ARRIVE_K >= 8) l6_bar_arrive(wg == 2 ? 1 : 2 + wg, 256);
+          l6_reg_dec<L6_PP_LO>();
+          relane();
+          repos();
         }
         // finished nodes
         if (K0 <= 3 && K0 + NP > 3) {
@@ -509,6 +614,7 @@ k_line6(const __grid_constant__ Dev d, const __grid_constant__ LineOps ops, doub
     e = e_next; valid = valid_next; fbits = fbits_next;
   }
   cp_async_wait<0>();
+  if (PP && wg == 0) l6_bar_sync(1, 256);   // takes the token warpgroup 2 passed on after the CTA's last flux part
 }
 
 // ---------------------------------------------------------------------------------------------- host side
@@ -517,10 +623,11 @@ k_line6(const __grid_constant__ Dev d, const __grid_constant__ LineOps ops, doub
 // batches of 2 and 5.3 ms with batches of 4 (local-memory spills of loop state, each reload an L2 round trip). The
 // kernel's time follows the SUM of the issue costs of its instructions, not the occupancy: 1 warp per scheduler already
 // reaches 70 % of the throughput of 2, and 3 add nothing (profiles/r1_line6_notes.md).
-template <int VFLUX, int SFLUX, bool SFV, int CTAS, int WARPS, int NP, bool RK = false, bool TOUT = false>
+template <int VFLUX, int SFLUX, bool SFV, int CTAS, int WARPS, int NP, bool RK = false, bool TOUT = false,
+          bool PP = false>
 static int line6_launch_t(const Dev& d, const LineOps& ops, double* du, const double* u, double t, const int* elems,
                           int64_t count, cudaStream_t stream, int sm_count, const RkArgs& rk = RkArgs{nullptr, 0, 0, 0}) {
-  auto kern = k_line6<VFLUX, SFLUX, SFV, WARPS, CTAS, NP, RK, TOUT>;
+  auto kern = k_line6<VFLUX, SFLUX, SFV, WARPS, CTAS, NP, RK, TOUT, PP>;
   static bool configured = false;
   if (!configured) {
     if (cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)l6_smem(WARPS)) != cudaSuccess)
@@ -548,6 +655,9 @@ static int line6_launch(const trixib200_config& c, const Dev& d, const LineOps& 
     // the shared tile (A/B measurements: 4.71 vs 4.66 ms at level 7)
     static const bool direct = getenv("TRIXIB200_LINE_SHAPE") && atoi(getenv("TRIXIB200_LINE_SHAPE")) == 8;
     if (direct && !sfv) return line6_launch_t<R, R, false, 2, 4, 8>(d, ops, du, u, t, elems, count, s, sm_count);
+    // TRIXIB200_LINE_SHAPE=12: the ping-pong shape (3 warpgroups, flux parts serialised by a token, setmaxnreg)
+    static const bool pp = getenv("TRIXIB200_LINE_SHAPE") && atoi(getenv("TRIXIB200_LINE_SHAPE")) == 12;
+    if (pp && !sfv) return line6_launch_t<R, R, false, 1, 12, 8, false, true, true>(d, ops, du, u, t, elems, count, s, sm_count);
     return sfv ? line6_launch_t<R, R, true, 2, 4, 8, false, true>(d, ops, du, u, t, elems, count, s, sm_count)
                : line6_launch_t<R, R, false, 2, 4, 8, false, true>(d, ops, du, u, t, elems, count, s, sm_count);
   }
