@@ -41,7 +41,8 @@ enum { TRIXIB200_VI_WEAK_FORM = 0, TRIXIB200_VI_FLUX_DIFFERENCING = 1, TRIXIB200
 enum { TRIXIB200_IND_DENSITY = 0, TRIXIB200_IND_PRESSURE = 1, TRIXIB200_IND_DENSITY_PRESSURE = 2 };
 enum { TRIXIB200_BC_PERIODIC = 0, TRIXIB200_BC_DIRICHLET_IC = 1,   /* BoundaryConditionDirichlet(initial_condition) */
        TRIXIB200_BC_SLIP_WALL = 2 };   /* boundary_condition_slip_wall, compressible Euler only */
-enum { TRIXIB200_IC_CONSTANT = 0, TRIXIB200_IC_CONVERGENCE_TEST = 1, TRIXIB200_IC_WEAK_BLAST_WAVE = 2,
+enum { TRIXIB200_IC_NONE = -1,           /* the caller's initial condition is not one of the enumerated ones */
+       TRIXIB200_IC_CONSTANT = 0, TRIXIB200_IC_CONVERGENCE_TEST = 1, TRIXIB200_IC_WEAK_BLAST_WAVE = 2,
        TRIXIB200_IC_DENSITY_WAVE = 3 };
 enum { TRIXIB200_SRC_NONE = 0, TRIXIB200_SRC_CONVERGENCE_TEST = 1 };
 

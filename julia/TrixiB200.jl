@@ -3,9 +3,11 @@
 # into libtrixib200.so (include/trixib200.h) instead of launching CUDA.jl-generated kernels.
 #
 # STATUS: written against the reference sources, NOT executed -- neither Julia nor Trixi.jl / CUDA.jl exist in the
-# build image or on the GPU boxes (DESIGN.md "Host language"). The identical call sequence is exercised through the
-# Python mirror (trixicuda.jl_b200/semidiscretization.py) by tests/test_gpu_parity.py. Every function cites the
-# reference definition it replaces.
+# build image or on the GPU boxes (DESIGN.md "Host language"). The identical call sequence -- including the argument
+# tuples Trixi's StepsizeCallback / AnalysisCallback pass (`mesh_equations_solver_cache` -> `wrap_array` -> `max_dt` /
+# `calc_error_norms` / `integrate` dispatching on the cache type) -- is exercised through the Python mirror
+# (trixicuda.jl_b200/semidiscretization.py) by tests/test_gpu_parity.py::test_callback_argument_tuples. Every function
+# cites the reference definition it replaces.
 module TrixiB200
 
 using Trixi
@@ -15,8 +17,13 @@ using Trixi: AbstractSemidiscretization, DG, TreeMesh, PerformanceCounter, nvari
              polydeg, have_nonconservative_terms, BoundaryConditionPeriodic, BoundaryConditionDirichlet,
              VolumeIntegralWeakForm, VolumeIntegralFluxDifferencing, VolumeIntegralShockCapturingHG,
              IndicatorHennemannGassner, LobattoLegendreBasis, LobattoLegendreMortarL2
+using Trixi: True, False, AbstractMesh, cons2cons, total_volume, analyze
+import Trixi: wrap_array, wrap_array_native, max_dt, calc_error_norms, integrate, integrate_via_indices,
+              analyze_integrals, mesh_equations_solver_cache      # extended exactly like reference src/TrixiCUDA.jl:56-62
 using SciMLBase: ODEProblem, FullSpecialize
-using CUDA: CuArray, CuVector, device, stream    # storage only: no CUDA.jl kernel runs on the rhs! path
+using StaticArrays: SVector
+import CUDA                                     # `CUDA.deviceid`, `CUDA.device`, `CUDA.stream`
+using CUDA: CuArray, CuVector, AbstractGPUArray   # storage only: no CUDA.jl kernel runs on the rhs! path
 
 export DGSEMGPU, SemidiscretizationHyperbolicGPU, semidiscretizeGPU
 
@@ -83,10 +90,21 @@ volume_integral_ids(vi::VolumeIntegralShockCapturingHG) =
 
 indicator_variable_id(f) = f === density ? Int32(0) : f === pressure ? Int32(1) :
                            f === density_pressure ? Int32(2) : error("libtrixib200: indicator variable not enumerated")
+# TRIXIB200_IC_NONE (-1) for anything else: the library then refuses Dirichlet(ic) boundaries, the device IC fill
+# and the device error norms instead of substituting another state; rhs! itself never needs the IC.
 initial_condition_id(f) = f === initial_condition_constant ? Int32(0) :
                           f === initial_condition_convergence_test ? Int32(1) :
                           f === initial_condition_weak_blast_wave ? Int32(2) :
                           f === initial_condition_density_wave ? Int32(3) : Int32(-1)
+# a Dirichlet boundary evaluates the enumerated IC on the device, so its boundary_value_function must BE the
+# semidiscretization's initial condition
+function check_dirichlet(bc::BoundaryConditionDirichlet, initial_condition)
+    bc.boundary_value_function === initial_condition ||
+        error("libtrixib200: BoundaryConditionDirichlet must use the semidiscretization's initial condition")
+    initial_condition_id(initial_condition) >= 0 ||
+        error("libtrixib200: BoundaryConditionDirichlet needs an enumerated initial condition")
+    return Int32(1)
+end
 source_terms_id(::Nothing) = Int32(0)
 source_terms_id(f) = f === source_terms_convergence_test ? Int32(1) :
                      error("libtrixib200: source terms $(f) are not enumerated")
@@ -103,6 +121,19 @@ end
 
 # ------------------------------------------------------------------------------------------------ semidiscretization
 # reference src/semidiscretization/semidiscretization_hyperbolic.jl:5-87
+# What `mesh_equations_solver_cache` hands to Trixi's callbacks in place of the reference's NamedTuple of CuArray
+# containers (reference src/solvers/cache.jl:130-212): the library handle plus Trixi's own CPU containers. Property
+# access falls through to the CPU cache, so Trixi code that only inspects containers (`nelements(dg, cache)`,
+# `cache.elements.inverse_jacobian`, `create_cache_analysis`) keeps working on host arrays, while the methods that touch
+# `u` dispatch on `cache::CacheB200` below and go to the device.
+struct CacheB200{CacheCPU}
+    handle::Ptr{Cvoid}             # trixib200_handle*
+    cpu::CacheCPU
+end
+Base.getproperty(c::CacheB200, s::Symbol) =
+    (s === :handle || s === :cpu) ? getfield(c, s) : getproperty(getfield(c, :cpu), s)
+Base.propertynames(c::CacheB200) = (:handle, :cpu, propertynames(getfield(c, :cpu))...)
+
 mutable struct SemidiscretizationHyperbolicGPU{Mesh, Equations, InitialCondition, BoundaryConditions, SourceTerms,
                                                Solver, CacheCPU} <: AbstractSemidiscretization
     mesh::Mesh
@@ -111,10 +142,11 @@ mutable struct SemidiscretizationHyperbolicGPU{Mesh, Equations, InitialCondition
     boundary_conditions::BoundaryConditions
     source_terms::SourceTerms
     solver::Solver
-    cache_gpu::Ptr{Cvoid}          # trixib200_handle*: replaces the NamedTuple of CuArray containers
+    cache_gpu::CacheB200{CacheCPU}  # same field names as the reference (semidiscretization_hyperbolic.jl:5-22)
     cache_cpu::CacheCPU
     performance_counter::PerformanceCounter
 end
+handle(semi::SemidiscretizationHyperbolicGPU) = semi.cache_gpu.handle
 
 function SemidiscretizationHyperbolicGPU(mesh::TreeMesh, equations, initial_condition, solver;
                                          source_terms = nothing,
@@ -136,7 +168,7 @@ function SemidiscretizationHyperbolicGPU(mesh::TreeMesh, equations, initial_cond
         i > 2nd && return Int32(0)
         bc = _bcs isa BoundaryConditionPeriodic ? _bcs : _bcs[i]
         bc isa BoundaryConditionPeriodic ? Int32(0) :
-        bc isa BoundaryConditionDirichlet ? Int32(1) :
+        bc isa BoundaryConditionDirichlet ? check_dirichlet(bc, initial_condition) :
         bc === Trixi.boundary_condition_slip_wall ? Int32(2) :
         error("libtrixib200: boundary condition not enumerated")
     end
@@ -146,8 +178,8 @@ function SemidiscretizationHyperbolicGPU(mesh::TreeMesh, equations, initial_cond
                  Int32(have_nonconservative_terms(equations) == Trixi.True()),
                  indicator === nothing ? Int32(2) : indicator_variable_id(indicator.variable),
                  indicator === nothing ? Int32(0) : Int32(indicator.alpha_smooth),
-                 bc_ids, max(initial_condition_id(initial_condition), Int32(0)), source_terms_id(source_terms),
-                 Int32(CUDA.deviceid(device())), Int32(rank), Int32(nranks), Int32(0),
+                 bc_ids, initial_condition_id(initial_condition), source_terms_id(source_terms),
+                 Int32(CUDA.deviceid(CUDA.device())), Int32(rank), Int32(nranks), Int32(0),
                  indicator === nothing ? 0.0 : indicator.alpha_max, indicator === nothing ? 0.0 : indicator.alpha_min,
                  hasproperty(equations, :gamma) ? equations.gamma : 0.0, adv,
                  hasproperty(equations, :c_h) ? equations.c_h : 0.0)
@@ -172,29 +204,45 @@ function SemidiscretizationHyperbolicGPU(mesh::TreeMesh, equations, initial_cond
     GC.@preserve keep check(ccall((:trixib200_create, LIB), Cint,
                                   (Ref{Config}, Ref{BasisHost}, Ref{MeshHost}, Ref{Ptr{Cvoid}}), cfg, bh, mh, handle))
     semi = SemidiscretizationHyperbolicGPU(mesh, equations, initial_condition, _bcs, source_terms, solver,
-                                           handle[], cache_cpu, PerformanceCounter())
-    finalizer(s -> ccall((:trixib200_destroy, LIB), Cint, (Ptr{Cvoid},), s.cache_gpu), semi)
+                                           CacheB200(handle[], cache_cpu), cache_cpu, PerformanceCounter())
+    finalizer(s -> ccall((:trixib200_destroy, LIB), Cint, (Ptr{Cvoid},), s.cache_gpu.handle), semi)
     return semi
 end
 
 @inline Base.ndims(semi::SemidiscretizationHyperbolicGPU) = ndims(semi.mesh)
-@inline Trixi.mesh_equations_solver_cache(semi::SemidiscretizationHyperbolicGPU) =
-    (semi.mesh, semi.equations, semi.solver, semi.cache_cpu)
+# reference src/semidiscretization/semidiscretization_hyperbolic.jl:91-95: the GPU cache goes to the callbacks
+@inline function mesh_equations_solver_cache(semi::SemidiscretizationHyperbolicGPU)
+    (; mesh, equations, solver, cache_gpu) = semi
+    return mesh, equations, solver, cache_gpu
+end
+
+# reference src/solvers/dg.jl:14-21,24-33: Trixi's `unsafe_wrap(Array, pointer(u_ode), ...)` cannot take a CuVector
+@inline function wrap_array(u_ode::AbstractGPUArray, mesh::AbstractMesh, equations, dg::DG, cache)
+    reshape(u_ode, nvariables(equations), ntuple(_ -> nnodes(dg), ndims(mesh))..., nelements(dg, cache))
+end
+@inline wrap_array_native(u_ode::AbstractGPUArray, mesh::AbstractMesh, equations, dg::DG, cache) =
+    wrap_array(u_ode, mesh, equations, dg, cache)
+
+devptr(a::AbstractGPUArray{Float64}) = reinterpret(Ptr{Float64}, pointer(a))
+set_stream!(h::Ptr{Cvoid}) = check(ccall((:trixib200_set_stream, LIB), Cint, (Ptr{Cvoid}, Int64), h,
+                                         reinterpret(Int64, CUDA.stream().handle)))
 
 # ------------------------------------------------------------------------------------------------ rhs!
 # reference src/solvers/solvers.jl:18-31 -> src/solvers/dg_3d.jl:895-925 (ten CUDA.jl kernel stages): one ccall.
 # `wrap_array` is a reshape, so the flat vectors go through unchanged (reference src/solvers/dg.jl:14-21).
 function rhs_gpu!(du_ode::CuVector{Float64}, u_ode::CuVector{Float64}, semi::SemidiscretizationHyperbolicGPU, t)
     # library work is ordered on CUDA.jl's task-local stream, like the broadcasts OrdinaryDiffEq issues around it
-    check(ccall((:trixib200_set_stream, LIB), Cint, (Ptr{Cvoid}, Int64), semi.cache_gpu,
-                reinterpret(Int64, stream().handle)))
-    check(ccall((:trixib200_rhs, LIB), Cint, (Ptr{Cvoid}, Ptr{Float64}, Ptr{Float64}, Float64), semi.cache_gpu,
-                reinterpret(Ptr{Float64}, pointer(du_ode)), reinterpret(Ptr{Float64}, pointer(u_ode)), t))
+    set_stream!(handle(semi))
+    check(ccall((:trixib200_rhs, LIB), Cint, (Ptr{Cvoid}, Ptr{Float64}, Ptr{Float64}, Float64), handle(semi),
+                devptr(du_ode), devptr(u_ode), t))
     return nothing
 end
+# Trixi's AnalysisCallback evaluates `rhs!(du_ode, u_ode, semi, t)` itself (entropy time derivative): same entry point
+Trixi.rhs!(du_ode::CuVector{Float64}, u_ode::CuVector{Float64}, semi::SemidiscretizationHyperbolicGPU, t) =
+    rhs_gpu!(du_ode, u_ode, semi, t)
 # host vectors (Trixi's CPU signature): upload, rhs!, download inside the library
 function rhs_gpu!(du_ode::Vector{Float64}, u_ode::Vector{Float64}, semi::SemidiscretizationHyperbolicGPU, t)
-    check(ccall((:trixib200_rhs_host, LIB), Cint, (Ptr{Cvoid}, Ptr{Float64}, Ptr{Float64}, Float64), semi.cache_gpu,
+    check(ccall((:trixib200_rhs_host, LIB), Cint, (Ptr{Cvoid}, Ptr{Float64}, Ptr{Float64}, Float64), handle(semi),
                 du_ode, u_ode, t))
     return nothing
 end
@@ -207,15 +255,75 @@ function semidiscretizeGPU(semi::SemidiscretizationHyperbolicGPU, tspan)
 end
 
 # ------------------------------------------------------------------------------------------------ StepsizeCallback
-# reference src/callbacks_step/stepsize_dg_3d.jl:20-45 (full device -> host copy of u + serial loop): device
-# reduction, one double comes back
-function Trixi.max_dt(u::CuArray{Float64}, t, mesh::TreeMesh, constant_speed, equations, dg::DG,
-                      semi::SemidiscretizationHyperbolicGPU)
-    out = Ref{Float64}(0.0)
-    check(ccall((:trixib200_max_dt, LIB), Cint, (Ptr{Cvoid}, Ptr{Float64}, Float64, Ref{Float64}), semi.cache_gpu,
-                reinterpret(Ptr{Float64}, pointer(u)), t, out))
-    return out[]
+# Trixi's `StepsizeCallback` calls (callbacks_step/stepsize.jl, `calculate_dt`):
+#     mesh, equations, solver, cache = mesh_equations_solver_cache(semi)
+#     u  = wrap_array(u_ode, mesh, equations, solver, cache)
+#     dt = cfl * max_dt(u, t, mesh, have_constant_speed(equations), equations, solver, cache)
+# The methods below have the reference's signatures (src/callbacks_step/stepsize_dg_{1,2,3}d.jl: `u::CuArray`, `True` /
+# `False`) with `cache::CacheB200`; the reference copies u to the host and loops serially, here one double comes back
+# from a device reduction (all ranks: ncclAllReduce(max) inside the library).
+for ND in 1:3, CS in (:True, :False)
+    @eval function max_dt(u::CuArray, t, mesh::TreeMesh{$ND}, constant_speed::$CS, equations, dg::DG,
+                          cache::CacheB200)
+        out = Ref{Float64}(0.0)
+        set_stream!(cache.handle)
+        check(ccall((:trixib200_max_dt, LIB), Cint, (Ptr{Cvoid}, Ptr{Float64}, Float64, Ref{Float64}), cache.handle,
+                    devptr(u), Float64(t), out))
+        return out[]
+    end
 end
+
+# ------------------------------------------------------------------------------------------------ AnalysisCallback
+# reference src/semidiscretization/semidiscretization_hyperbolic.jl:97-105 and src/callbacks_step/analysis_dg_{1,2,3}d.jl
+function calc_error_norms(func, u_ode, t, analyzer, semi::SemidiscretizationHyperbolicGPU, cache_analysis)
+    (; mesh, equations, initial_condition, solver, cache_gpu) = semi
+    u = wrap_array(u_ode, mesh, equations, solver, cache_gpu)
+    calc_error_norms(func, u, t, analyzer, mesh, equations, initial_condition, solver, cache_gpu, cache_analysis)
+end
+# L2 / Linf errors of the conserved variables against an enumerated initial condition: on the device
+# (trixib200_calc_error_norms interpolates u and the node coordinates to the analyzer's nodes like Trixi's
+# multiply_dimensionwise!, evaluates the IC there and reduces deterministically). Everything else takes the
+# reference's route (src/callbacks_step/analysis_dg_3d.jl:52-54: host copy, Trixi's CPU method on the CPU containers).
+function calc_error_norms(func, u::CuArray, t, analyzer, mesh::TreeMesh, equations, initial_condition, dg::DG,
+                          cache::CacheB200, cache_analysis)
+    if func === cons2cons && initial_condition_id(initial_condition) >= 0
+        nv = nvariables(equations)
+        l2, linf = zeros(nv), zeros(nv)
+        V = permutedims(Array{Float64}(analyzer.vandermonde))     # C wants [n_analysis][nnodes] row-major
+        w = Array{Float64}(analyzer.weights)
+        set_stream!(cache.handle)
+        check(ccall((:trixib200_calc_error_norms, LIB), Cint,
+                    (Ptr{Cvoid}, Ptr{Float64}, Float64, Int32, Ptr{Float64}, Ptr{Float64}, Float64, Ptr{Float64},
+                     Ptr{Float64}), cache.handle, devptr(u), Float64(t), Int32(length(w)), V, w,
+                    Float64(total_volume(mesh)), l2, linf))
+        return SVector{nv}(l2), SVector{nv}(linf)
+    end
+    return calc_error_norms(func, Array(u), t, analyzer, mesh, equations, initial_condition, dg, cache.cpu,
+                            cache_analysis)
+end
+# domain integrals: the conserved variables on the device, any other functional through a host copy as in the
+# reference (src/callbacks_step/analysis_dg_3d.jl:1-43)
+function integrate(func::Func, u::CuArray, mesh::TreeMesh, equations, dg::DG, cache::CacheB200;
+                   normalize = true) where {Func}
+    if func === cons2cons
+        out = zeros(nvariables(equations))
+        set_stream!(cache.handle)
+        check(ccall((:trixib200_integrate, LIB), Cint, (Ptr{Cvoid}, Ptr{Float64}, Int32, Float64, Ptr{Float64}),
+                    cache.handle, devptr(u), Int32(normalize), Float64(total_volume(mesh)), out))
+        return SVector{length(out)}(out)
+    end
+    return integrate(func, Array(u), mesh, equations, dg, cache.cpu; normalize)
+end
+integrate_via_indices(func::Func, u::CuArray, mesh::TreeMesh, equations, dg::DG, cache::CacheB200, args...;
+                      normalize = true) where {Func} =
+    integrate_via_indices(func, Array(u), mesh, equations, dg, cache.cpu, args...; normalize)
+# reference src/callbacks_step/analysis.jl:1-36: the analysis integrals are arbitrary Julia functionals of (du, u):
+# ONE host copy for all of them (the reference copies per quantity), then Trixi's own `analyze`
+function analyze_integrals(analysis_integrals::NTuple{N, Any}, io, du::CuArray, u::CuArray, t,
+                           semi::SemidiscretizationHyperbolicGPU) where {N}
+    analyze_integrals(analysis_integrals, io, Array(du), Array(u), t, semi)
+end
+analyze_integrals(::Tuple{}, io, du::CuArray, u::CuArray, t, semi::SemidiscretizationHyperbolicGPU) = nothing
 
 # ------------------------------------------------------------------------------------------------ fused RK stages
 # Optional fast path (SURVEY.md section 8(f) row 1): OrdinaryDiffEq's `perform_step!` for `CarpenterKennedy2N54` is
@@ -225,23 +333,19 @@ end
 # Trixi's StepsizeCallback logic (`dt = cfl * max_dt(u, ...)`).
 function rk2n_stage!(u_out::CuVector{Float64}, u_in::CuVector{Float64}, tmp::CuVector{Float64},
                      semi::SemidiscretizationHyperbolicGPU, t, a, b, dt)
-    check(ccall((:trixib200_set_stream, LIB), Cint, (Ptr{Cvoid}, Int64), semi.cache_gpu,
-                reinterpret(Int64, stream().handle)))
+    set_stream!(handle(semi))
     check(ccall((:trixib200_rk2n_stage, LIB), Cint,
                 (Ptr{Cvoid}, Ptr{Float64}, Ptr{Float64}, Ptr{Float64}, Float64, Float64, Float64, Float64),
-                semi.cache_gpu, reinterpret(Ptr{Float64}, pointer(u_out)), reinterpret(Ptr{Float64}, pointer(u_in)),
-                reinterpret(Ptr{Float64}, pointer(tmp)), t, a, b, dt))
+                handle(semi), devptr(u_out), devptr(u_in), devptr(tmp), t, a, b, dt))
     return nothing
 end
 function step_ck2n54!(u::CuVector{Float64}, u_alt::CuVector{Float64}, tmp::CuVector{Float64},
                       semi::SemidiscretizationHyperbolicGPU, t, dt)
     in_alt = Ref{Cint}(0)
-    check(ccall((:trixib200_set_stream, LIB), Cint, (Ptr{Cvoid}, Int64), semi.cache_gpu,
-                reinterpret(Int64, stream().handle)))
+    set_stream!(handle(semi))
     check(ccall((:trixib200_rk2n_step_ck54, LIB), Cint,
-                (Ptr{Cvoid}, Ptr{Float64}, Ptr{Float64}, Ptr{Float64}, Float64, Float64, Ref{Cint}), semi.cache_gpu,
-                reinterpret(Ptr{Float64}, pointer(u)), reinterpret(Ptr{Float64}, pointer(u_alt)),
-                reinterpret(Ptr{Float64}, pointer(tmp)), t, dt, in_alt))
+                (Ptr{Cvoid}, Ptr{Float64}, Ptr{Float64}, Ptr{Float64}, Float64, Float64, Ref{Cint}), handle(semi),
+                devptr(u), devptr(u_alt), devptr(tmp), t, dt, in_alt))
     return in_alt[] == 1 ? u_alt : u
 end
 

@@ -424,9 +424,11 @@ inline void initial_condition(int ic, const double* x, double t, const EqParams&
   }
   if (p.kind == EQ_EULER) {
     if (ic == IC_CONSTANT) {
-      double q[5] = {1.0, 0.1, -0.2, 0.7, 10.0};
-      if (nd < 3) q[nd + 1] = 10.0;
-      euler_prim2cons(q, p, u);
+      // Trixi initial_condition_constant: conservative (rho, rho_v..., rho_e) = (1.0, 0.1[, -0.2[, 0.7]], 10.0)
+      const double c0[3] = {0.1, -0.2, 0.7};
+      u[0] = 1.0;
+      for (int d = 0; d < nd; ++d) u[1 + d] = c0[d];
+      u[nd + 1] = 10.0;
       return;
     }
     if (ic == IC_CONVERGENCE_TEST) {
@@ -440,12 +442,13 @@ inline void initial_condition(int ic, const double* x, double t, const EqParams&
       return;
     }
     if (ic == IC_DENSITY_WAVE) {
-      // smooth synthetic state: rho = 1 + 0.5 sin(pi (x+y+z - t*(v1+v2+v3))), v = (0.1,0.2,0.3), p = 20
+      // Trixi initial_condition_density_wave (1D v = 0.1; 2D v = (0.1, 0.2)): rho = 1 + 0.98 sinpi(2 (sum x - t sum v)),
+      // p = 20; Trixi has no 3D method, the 3D case continues the pattern with v3 = 0.3
       const double v[3] = {0.1, 0.2, 0.3};
-      double s = 0;
-      for (int d = 0; d < nd; ++d) s += x[d] - v[d] * t;
+      double s = 0, vs = 0;
+      for (int d = 0; d < nd; ++d) { s += x[d]; vs += v[d]; }
       double q[5];
-      q[0] = 1 + 0.5 * std::sin(M_PI * s);
+      q[0] = 1 + 0.98 * std::sin(M_PI * (2 * (s - t * vs)));
       for (int d = 0; d < nd; ++d) q[1 + d] = v[d];
       q[nd + 1] = 20.0;
       euler_prim2cons(q, p, u);
@@ -478,11 +481,9 @@ inline void initial_condition(int ic, const double* x, double t, const EqParams&
   }
   // GLM-MHD 3D
   if (ic == IC_CONSTANT) {
-    double q[9] = {1.0, 0.1, -0.2, 0.3, 1.5, 0.4, -0.3, 0.2, 0.05};
-    u[0] = q[0]; u[1] = q[0] * q[1]; u[2] = q[0] * q[2]; u[3] = q[0] * q[3];
-    u[5] = q[5]; u[6] = q[6]; u[7] = q[7]; u[8] = q[8];
-    u[4] = q[4] / (p.gamma - 1) + 0.5 * (u[1] * q[1] + u[2] * q[2] + u[3] * q[3]) +
-           0.5 * (q[5] * q[5] + q[6] * q[6] + q[7] * q[7]) + 0.5 * q[8] * q[8];
+    // Trixi initial_condition_constant(IdealGlmMhdEquations3D): the conservative state
+    const double c0[9] = {1.0, 0.1, -0.2, -0.5, 50.0, 3.0, -1.2, 0.5, 0.0};
+    for (int v = 0; v < 9; ++v) u[v] = c0[v];
     return;
   }
   if (ic == IC_WEAK_BLAST_WAVE) {

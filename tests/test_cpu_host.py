@@ -167,3 +167,16 @@ def test_halo_exchange_world_size_2_gloo():
                          timeout=600)
     assert res.returncode == 0, res.stdout[-3000:] + res.stderr[-3000:]
     assert res.stdout.count("HALO_OK") == 2, res.stdout[-2000:]
+
+
+def test_callback_methods_refuse_a_cpu_cache():
+    """`max_dt` / `integrate` exist only for the cache `mesh_equations_solver_cache(semi)` returns (Julia: dispatch on
+    `cache::CacheB200`); anything else must fail loudly instead of falling into a CPU method."""
+    import trixib200 as T
+    eq = T.CompressibleEulerEquations3D(1.4)
+    for call in (lambda: T.max_dt(None, 0.0, None, False, eq, None, object()),
+                 lambda: T.integrate(T.cons2cons, None, None, eq, None, {"elements": None})):
+        with pytest.raises(TypeError):
+            call()
+    with pytest.raises(NotImplementedError):
+        T.integrate(lambda u, e: u, None, None, eq, None, None)

@@ -24,7 +24,10 @@ from .equations import (
 from .solver import (DGSEMGPU, SurfaceIntegralWeakForm, VolumeIntegralWeakForm, VolumeIntegralFluxDifferencing,
                      VolumeIntegralShockCapturingHG, IndicatorHennemannGassner)
 from .semidiscretization import (SemidiscretizationHyperbolicGPU, semidiscretizeGPU, rhs_gpu_, wrap_array, max_dt,
-                                 ODEProblem)
-from .ode import (CarpenterKennedy2N54, StepsizeCallback, AnalysisCallback, CallbackSet, solve, calc_error_norms)
+                                 ODEProblem, CacheB200, mesh_equations_solver_cache, cons2cons, integrate)
+from . import semidiscretization as _semi_mod
+from .ode import (CarpenterKennedy2N54, StepsizeCallback, AnalysisCallback, CallbackSet, solve, calc_error_norms,
+                  calculate_dt)
+calc_error_norms_gpu = _semi_mod.calc_error_norms
 
 __all__ = [n for n in dir() if not n.startswith("_")]

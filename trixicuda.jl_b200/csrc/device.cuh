@@ -76,4 +76,23 @@ template <int ND> TB_D int mortar_small_row(int q) {
   return q == 0 ? 1 : 0;
 }
 
+// cudaFuncSetAttribute is per device / context: remember per kernel WHICH devices have been configured (a second
+// handle on another GPU of the same process otherwise launches without the shared-memory opt-in).
+struct DeviceOnce {
+  unsigned long long mask = 0;
+  bool need() {
+    int dev = 0;
+    cudaGetDevice(&dev);
+    const unsigned long long bit = 1ull << (dev & 63);
+    if (mask & bit) return false;
+    mask |= bit;
+    return true;
+  }
+  void undo() {
+    int dev = 0;
+    cudaGetDevice(&dev);
+    mask &= ~(1ull << (dev & 63));
+  }
+};
+
 }  // namespace tb

@@ -298,11 +298,13 @@ template <int ND> struct EqEuler {
   TB_D static void initial_condition(int ic, const double* x, double t, const EqPrm& p, double* u) {
     double q[NV];
     if (ic == TRIXIB200_IC_CONSTANT) {
-      const double q0[5] = {1.0, 0.1, -0.2, 0.7, 10.0};
+      // Trixi initial_condition_constant: the CONSERVATIVE state (rho, rho_v1[, rho_v2[, rho_v3]], rho_e) =
+      // (1.0, 0.1[, -0.2[, 0.7]], 10.0)
+      const double c0[3] = {0.1, -0.2, 0.7};
+      u[0] = 1.0;
 #pragma unroll
-      for (int v = 0; v < NV; ++v) q[v] = q0[v];
-      q[ND + 1] = 10.0;
-      prim2cons(q, p, u);
+      for (int d = 0; d < ND; ++d) u[1 + d] = c0[d];
+      u[ND + 1] = 10.0;
       return;
     }
     if (ic == TRIXIB200_IC_CONVERGENCE_TEST) {
@@ -318,11 +320,13 @@ template <int ND> struct EqEuler {
       return;
     }
     if (ic == TRIXIB200_IC_DENSITY_WAVE) {
+      // Trixi initial_condition_density_wave (1D: v = 0.1; 2D: v = (0.1, 0.2)): rho = 1 + 0.98 sinpi(2 (sum x - t sum v)),
+      // p = 20. Trixi has no 3D method; the 3D case continues the pattern with v3 = 0.3 (synthetic smooth timing state).
       const double v[3] = {0.1, 0.2, 0.3};
-      double s = 0;
+      double s = 0, vs = 0;
 #pragma unroll
-      for (int d = 0; d < ND; ++d) s += x[d] - v[d] * t;
-      q[0] = 1 + 0.5 * sin(M_PI * s);
+      for (int d = 0; d < ND; ++d) { s += x[d]; vs += v[d]; }
+      q[0] = 1 + 0.98 * sinpi(2 * (s - t * vs));
 #pragma unroll
       for (int d = 0; d < ND; ++d) q[1 + d] = v[d];
       q[ND + 1] = 20.0;
@@ -579,10 +583,10 @@ struct EqMhd3 {
   TB_D static void initial_condition(int ic, const double* x, double t, const EqPrm& p, double* u) {
     double q[9];
     if (ic == TRIXIB200_IC_CONSTANT) {
-      const double q0[9] = {1.0, 0.1, -0.2, 0.3, 1.5, 0.4, -0.3, 0.2, 0.05};
+      // Trixi initial_condition_constant(IdealGlmMhdEquations3D): the conservative state
+      const double c0[9] = {1.0, 0.1, -0.2, -0.5, 50.0, 3.0, -1.2, 0.5, 0.0};
 #pragma unroll
-      for (int v = 0; v < 9; ++v) q[v] = q0[v];
-      prim2cons(q, p, u);
+      for (int v = 0; v < 9; ++v) u[v] = c0[v];
       return;
     }
     if (ic == TRIXIB200_IC_WEAK_BLAST_WAVE) {

@@ -325,11 +325,10 @@ static int fused_launch_t(const Dev& d, double* du, const double* u, double t, c
                           cudaStream_t stream) {
   using C = FusedCfg<Eq, VI>;
   auto kern = k_fused<Eq, VI, VFLUX, SFLUX, FFLUX, NONCONS>;
-  static bool configured = false;
-  if (!configured) {
+  static DeviceOnce configured;
+  if (configured.need()) {
     if (cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)C::SMEM) != cudaSuccess)
-      return TRIXIB200_ECUDA;
-    configured = true;
+      { configured.undo(); return TRIXIB200_ECUDA; }
   }
   if (count <= 0) return 0;
   unsigned blocks = (unsigned)((count + C::EPB - 1) / C::EPB);

@@ -514,11 +514,10 @@ template <int VFLUX, int SFLUX, int WARPS>
 static int line3d_launch_t(const Dev& d, const LineOps& ops, double* du, const double* u, double t, const int* elems,
                            int64_t count, cudaStream_t stream, int sm_count) {
   auto kern = k_line3d<VFLUX, SFLUX, WARPS>;
-  static bool configured = false;
-  if (!configured) {
+  static DeviceOnce configured;
+  if (configured.need()) {
     if (cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)l3_smem(WARPS)) != cudaSuccess)
-      return TRIXIB200_ECUDA;
-    configured = true;
+      { configured.undo(); return TRIXIB200_ECUDA; }
   }
   if (count <= 0) return 0;
   const int64_t npairs = (count + 1) / 2;

@@ -628,12 +628,11 @@ template <int VFLUX, int SFLUX, bool SFV, int CTAS, int WARPS, int NP, bool RK =
 static int line6_launch_t(const Dev& d, const LineOps& ops, double* du, const double* u, double t, const int* elems,
                           int64_t count, cudaStream_t stream, int sm_count, const RkArgs& rk = RkArgs{nullptr, 0, 0, 0}) {
   auto kern = k_line6<VFLUX, SFLUX, SFV, WARPS, CTAS, NP, RK, TOUT, PP>;
-  static bool configured = false;
-  if (!configured) {
+  static DeviceOnce configured;
+  if (configured.need()) {
     if (cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)l6_smem(WARPS)) != cudaSuccess)
       return TRIXIB200_ECUDA;
     cudaFuncSetAttribute(kern, cudaFuncAttributePreferredSharedMemoryCarveout, 100);
-    configured = true;
   }
   if (count <= 0) return 0;
   const int64_t npairs = (count + 1) / 2;

@@ -567,7 +567,8 @@ __global__ void k_rk2n_update(double* __restrict__ u, double* __restrict__ tmp, 
   int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   int64_t stride = (int64_t)gridDim.x * blockDim.x;
   for (; i < n; i += stride) {
-    double t = a * tmp[i] + dt * du[i];
+    // a == 0 (first stage of a 2N scheme): tmp is not read, it may be uninitialised memory
+    double t = a != 0.0 ? fma(a, tmp[i], dt * du[i]) : dt * du[i];
     tmp[i] = t;
     u[i] += b * t;
   }

@@ -250,11 +250,10 @@ static int warp3d_launch_t(const Dev& d, double* du, const double* u, double t, 
                            cudaStream_t stream, int sm_count) {
   using C = Warp3Cfg<Eq>;
   auto kern = k_warp3d<Eq, VFLUX, SFLUX>;
-  static bool configured = false;
-  if (!configured) {
+  static DeviceOnce configured;
+  if (configured.need()) {
     if (cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)C::SMEM) != cudaSuccess)
-      return TRIXIB200_ECUDA;
-    configured = true;
+      { configured.undo(); return TRIXIB200_ECUDA; }
   }
   if (count <= 0) return 0;
   int64_t want = (count + W3_WARPS - 1) / W3_WARPS;

@@ -313,6 +313,16 @@ static inline unsigned nblk(int64_t n, int t) { return (unsigned)((n + t - 1) / 
     else { constexpr int ND = 3; __VA_ARGS__; }                                                \
   } while (0)
 
+// enumerated initial conditions per equation set (TRIXIB200_IC_NONE = -1: the caller's IC is not enumerated; the
+// device then refuses Dirichlet(ic) boundaries, fill_initial_condition and calc_error_norms instead of silently
+// substituting another state)
+static bool ic_supported(const trixib200_config& c) {
+  const int ic = c.initial_condition;
+  if (ic < TRIXIB200_IC_CONSTANT || ic > TRIXIB200_IC_DENSITY_WAVE) return false;
+  if (ic == TRIXIB200_IC_DENSITY_WAVE) return c.equations == TRIXIB200_EQ_EULER;
+  if (ic == TRIXIB200_IC_WEAK_BLAST_WAVE) return c.equations != TRIXIB200_EQ_ADVECTION;
+  return true;
+}
 static bool flux_supported(const trixib200_config& c, int k) {
   if (c.equations == TRIXIB200_EQ_ADVECTION) return EqAdvection<1>::supports_flux(k);
   if (c.equations == TRIXIB200_EQ_EULER) return EqEuler<1>::supports_flux(k);
@@ -378,6 +388,9 @@ static int create_impl(const trixib200_config* cfg, const trixib200_basis_host* 
   for (int q = 0; q < 2 * c.ndim; ++q) {
     const int bc = c.boundary_conditions[q];
     if (bc < TRIXIB200_BC_PERIODIC || bc > TRIXIB200_BC_SLIP_WALL) return fail(TRIXIB200_EUNSUPPORTED, "unknown boundary condition id");
+    if (bc == TRIXIB200_BC_DIRICHLET_IC && !ic_supported(c))
+      return fail(TRIXIB200_EUNSUPPORTED, "BoundaryConditionDirichlet needs an enumerated initial condition "
+                                          "(config.initial_condition is TRIXIB200_IC_NONE or unknown for these equations)");
     if (bc == TRIXIB200_BC_SLIP_WALL && c.equations != TRIXIB200_EQ_EULER)
       return fail(TRIXIB200_EUNSUPPORTED, "boundary_condition_slip_wall only for compressible Euler");
   }
@@ -680,16 +693,25 @@ static int halo_begin(trixib200_handle* h, const double* u) {
     }
   }
   size_t per = (size_t)d.nv * d.nf;
-  g_nccl.GroupStart();
+  auto nccl_err = [](const char* what, int rc) {
+    return fail(TRIXIB200_ECOMM, std::string(what) + ": " + (g_nccl.GetErrorString ? g_nccl.GetErrorString(rc) : "?"));
+  };
+  int rc = g_nccl.GroupStart();
+  if (rc != 0) return nccl_err("ncclGroupStart", rc);
   size_t off = 0;
+  int rc_first = 0;
+  const char* what_first = nullptr;
   for (size_t k = 0; k < h->peers.size(); ++k) {
     size_t cnt = per * (size_t)h->peer_count[k];
-    g_nccl.Send(d.halo_send + off, cnt, NCCL_FLOAT64, h->peers[k], h->comm, h->comm_stream);
-    g_nccl.Recv((void*)(d.halo_recv + off), cnt, NCCL_FLOAT64, h->peers[k], h->comm, h->comm_stream);
+    rc = g_nccl.Send(d.halo_send + off, cnt, NCCL_FLOAT64, h->peers[k], h->comm, h->comm_stream);
+    if (rc != 0 && !rc_first) { rc_first = rc; what_first = "ncclSend"; }
+    rc = g_nccl.Recv((void*)(d.halo_recv + off), cnt, NCCL_FLOAT64, h->peers[k], h->comm, h->comm_stream);
+    if (rc != 0 && !rc_first) { rc_first = rc; what_first = "ncclRecv"; }
     off += cnt;
   }
-  int rc = g_nccl.GroupEnd();
-  if (rc != 0) return fail(TRIXIB200_ECOMM, std::string("ncclGroupEnd: ") + (g_nccl.GetErrorString ? g_nccl.GetErrorString(rc) : "?"));
+  rc = g_nccl.GroupEnd();       // always closed, also after a failed send / recv
+  if (rc_first != 0) return nccl_err(what_first, rc_first);
+  if (rc != 0) return nccl_err("ncclGroupEnd", rc);
   CUDA_TRY(cudaEventRecord(h->ev_halo, h->comm_stream));
   return 0;
 }
@@ -1066,6 +1088,7 @@ extern "C" int trixib200_fill_initial_condition(trixib200_handle* h, double* u, 
   if (!h || !u) return fail(TRIXIB200_EINVAL, "null argument");
   CUDA_TRY(cudaSetDevice(h->cfg.device));
   Dev& d = h->d;
+  if (!ic_supported(h->cfg)) return fail(TRIXIB200_EUNSUPPORTED, "fill_initial_condition: the initial condition is not enumerated");
   if (!d.node_coords && !d.centers) return fail(TRIXIB200_EINVAL, "fill_initial_condition needs node_coordinates or cell_centers");
   TB_DISPATCH_EQ(h, LAUNCH(h, k_fill_ic<Eq>, d.E * d.nn, 128, 0, d, u, t));
   CUDA_TRY(cudaGetLastError());
@@ -1169,7 +1192,8 @@ extern "C" int trixib200_calc_error_norms(trixib200_handle* h, const double* u, 
   CUDA_TRY(cudaSetDevice(h->cfg.device));
   Dev& d = h->d;
   const int NA = n_analysis, nv = d.nv;
-  if (NA < 1 || NA > 2 * MAXN) return fail(TRIXIB200_EINVAL, "calc_error_norms: 1 <= n_analysis <= 16");
+  if (NA < d.N || NA > 2 * MAXN) return fail(TRIXIB200_EINVAL, "calc_error_norms: nnodes <= n_analysis <= 16");
+  if (!ic_supported(h->cfg)) return fail(TRIXIB200_EUNSUPPORTED, "calc_error_norms: the initial condition is not enumerated");
   if (!d.node_coords && !d.centers) return fail(TRIXIB200_EINVAL, "calc_error_norms needs node_coordinates or cell_centers");
   if (!(total_volume > 0)) return fail(TRIXIB200_EINVAL, "calc_error_norms: total_volume must be positive");
   const size_t smem = analysis_smem_doubles(d.ndim, d.N, NA, nv) * sizeof(double);

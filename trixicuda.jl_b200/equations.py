@@ -171,20 +171,19 @@ class InitialCondition(_Named):
 
 
 def _ic_constant(x, t, eq):
+    """Trixi `initial_condition_constant`: a CONSERVATIVE state (Euler (1, 0.1[, -0.2[, 0.7]], 10); GLM-MHD
+    (1, 0.1, -0.2, -0.5, 50, 3, -1.2, 0.5, 0); advection 2)."""
     shape = x.shape[1:]
     if eq.kind == _lib.EQ_ADVECTION:
         return np.full((1,) + shape, 2.0)
     if eq.kind == _lib.EQ_EULER:
-        q = np.empty((eq.nvars,) + shape)
-        vals = [1.0, 0.1, -0.2, 0.7, 10.0]
-        for v in range(eq.nvars):
-            q[v] = vals[v]
-        q[eq.ndim + 1] = 10.0
-        return eq.prim2cons(q)
-    q = np.empty((9,) + shape)
-    for v, val in enumerate([1.0, 0.1, -0.2, 0.3, 1.5, 0.4, -0.3, 0.2, 0.05]):
-        q[v] = val
-    return eq.prim2cons(q)
+        vals = [1.0] + [0.1, -0.2, 0.7][: eq.ndim] + [10.0]
+    else:
+        vals = [1.0, 0.1, -0.2, -0.5, 50.0, 3.0, -1.2, 0.5, 0.0]
+    u = np.empty((eq.nvars,) + shape)
+    for v, val in enumerate(vals):
+        u[v] = val
+    return u
 
 
 def _ic_convergence_test(x, t, eq):
@@ -260,15 +259,17 @@ def _ic_weak_blast_wave(x, t, eq):
 
 
 def _ic_density_wave(x, t, eq):
+    """Trixi `initial_condition_density_wave` (1D: v = 0.1, 2D: v = (0.1, 0.2)): rho = 1 + 0.98 sinpi(2 (sum x - t sum v)),
+    p = 20. Trixi has no 3D method: the 3D case continues the pattern with v3 = 0.3 (smooth synthetic timing state)."""
     if eq.kind != _lib.EQ_EULER:
         raise NotImplementedError("initial_condition_density_wave needs compressible Euler")
     nd = eq.ndim
-    v = (0.1, 0.2, 0.3)
+    v = (0.1, 0.2, 0.3)[:nd]
     s = 0.0
     for d in range(nd):
-        s = s + (x[d] - v[d] * t)
+        s = s + x[d]
     q = np.empty((nd + 2,) + x.shape[1:])
-    q[0] = 1 + 0.5 * np.sin(np.pi * s)
+    q[0] = 1 + 0.98 * np.sin(np.pi * (2 * (s - t * sum(v))))
     for d in range(nd):
         q[1 + d] = v[d]
     q[nd + 1] = 20.0

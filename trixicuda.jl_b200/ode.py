@@ -29,6 +29,15 @@ class StepsizeCallback:
         self.cfl = float(cfl)
 
 
+def calculate_dt(u_ode, t, cfl_number, semi):
+    """Trixi `calculate_dt(u_ode, t, cfl_number, semi)` (callbacks_step/stepsize.jl), the body of StepsizeCallback:
+    the argument tuple below is what reaches the reference's / the shim's `max_dt` method."""
+    from .semidiscretization import mesh_equations_solver_cache, wrap_array, max_dt
+    mesh, equations, solver, cache = mesh_equations_solver_cache(semi)
+    u = wrap_array(u_ode, mesh, equations, solver, cache)
+    return cfl_number * max_dt(u, t, mesh, equations.have_constant_speed(), equations, solver, cache)
+
+
 class AnalysisCallback:
     """`AnalysisCallback(semi, interval=...)`. on_device=True evaluates the error norms with the library's reduction
     kernels (trixib200_calc_error_norms; enumerated initial conditions, any number of ranks) instead of copying u to
@@ -112,7 +121,7 @@ def solve(ode, alg=None, dt=1.0, callback=None, maxiters=10 ** 9, fused_stages=F
         ana_cb(u, t)
     while t < t_end and nsteps < maxiters:
         if step_cb is not None:
-            dt = step_cb.cfl * semi.max_dt(u, t)
+            dt = calculate_dt(u, t, step_cb.cfl, semi)
         if t + dt > t_end or abs(t + dt - t_end) < 100 * 2.2e-16 * max(1.0, abs(t_end)):
             dt = t_end - t
         if fused_stages:

@@ -26,6 +26,23 @@ def _torch():
     return torch
 
 
+class CacheB200:
+    """What `mesh_equations_solver_cache` hands to the callbacks (Julia: `CacheB200`, julia/TrixiB200.jl): the library
+    handle plus Trixi's CPU containers; attribute access falls through to the CPU containers (`cache.elements`, ...).
+    Replaces the reference's NamedTuple of CuArray containers (reference src/solvers/cache.jl:130-212)."""
+
+    def __init__(self, semi):
+        self._semi = semi
+        self.cpu = semi.cache_cpu
+
+    @property
+    def handle(self):
+        return self._semi._h
+
+    def __getattr__(self, name):
+        return getattr(self.cpu, name)
+
+
 class SemidiscretizationHyperbolicGPU:
     def __init__(self, mesh: TreeMesh, equations, initial_condition, solver, source_terms=None,
                  boundary_conditions=boundary_condition_periodic, staged_only=False, no_warp_kernel=False, no_line_kernel=False,
@@ -42,6 +59,7 @@ class SemidiscretizationHyperbolicGPU:
         self.device_index = torch.cuda.current_device() if device is None else int(device)
         self.device = torch.device("cuda", self.device_index)
         self.cache_cpu = init_containers(mesh, solver.basis.nodes)   # what Trixi's init_* give the Julia shim
+        self.cache_gpu = CacheB200(self)
         self._create(staged_only, comm_id, node_coordinates, no_warp_kernel, no_line_kernel)
 
     # ------------------------------------------------------------------ handle construction
@@ -75,7 +93,7 @@ class SemidiscretizationHyperbolicGPU:
         if ic_for_bc is not None and isinstance(ic, InitialCondition) and ic_for_bc is not ic:
             raise NotImplementedError("BoundaryConditionDirichlet must use the semidiscretization's initial condition")
         ic_enum = ic_for_bc if ic_for_bc is not None else ic
-        cfg.initial_condition = ic_enum.code if isinstance(ic_enum, InitialCondition) else 0
+        cfg.initial_condition = ic_enum.code if isinstance(ic_enum, InitialCondition) else -1   # TRIXIB200_IC_NONE
         if self.source_terms is None:
             cfg.source_terms = _lib.SRC["none"]
         elif getattr(self.source_terms, "code", None) is not None:
@@ -318,12 +336,55 @@ def semidiscretizeGPU(semi, tspan, on_device_ic=False):
     return ODEProblem(rhs_gpu_, u0, tuple(tspan), semi)
 
 
-def wrap_array(u_ode, semi):
-    """`reshape(u_ode, nvars, N.., nelements)`; torch is row-major so the view is [element, (k, j,) i, v]."""
+def mesh_equations_solver_cache(semi):
+    """reference src/semidiscretization/semidiscretization_hyperbolic.jl:91-95: the GPU cache goes to the callbacks."""
+    return semi.mesh, semi.equations, semi.solver, semi.cache_gpu
+
+
+def wrap_array(u_ode, mesh_or_semi, equations=None, dg=None, cache=None):
+    """`wrap_array(u_ode, mesh, equations, dg, cache)` = `reshape(u_ode, nvars, N.., nelements)` (reference
+    src/solvers/dg.jl:14-21); torch is row-major so the view is [element, (k, j,) i, v]. `wrap_array(u_ode, semi)` is
+    accepted as a shorthand."""
+    semi = mesh_or_semi if cache is None else cache._semi
     n, nd = semi.nnodes, semi.mesh.ndim
     return u_ode.view((semi.nelements,) + (n,) * nd + (semi.nvars,))
 
 
-def max_dt(u, t, mesh, constant_speed, equations, solver, cache):
-    """Signature of the reference method (stepsize_dg_3d.jl:1-45); `cache` is the semidiscretization here."""
-    return cache.max_dt(u, t)
+def _need_cache(cache, what):
+    if not isinstance(cache, CacheB200):
+        raise TypeError(f"{what}: the cache must be the CacheB200 returned by mesh_equations_solver_cache(semi) "
+                        f"(got {type(cache).__name__}); there is no CPU method behind this name")
+    return cache._semi
+
+
+def max_dt(u, t, mesh, constant_speed, equations, dg, cache):
+    """The reference's method signature (src/callbacks_step/stepsize_dg_3d.jl:1-45), exactly as Trixi's
+    StepsizeCallback calls it: `max_dt(u, t, mesh, have_constant_speed(equations), equations, solver, cache)` with
+    (mesh, equations, solver, cache) = mesh_equations_solver_cache(semi) and u = wrap_array(u_ode, ...)."""
+    semi = _need_cache(cache, "max_dt")
+    if mesh is not semi.mesh or equations is not semi.equations or dg is not semi.solver:
+        raise ValueError("max_dt: mesh / equations / solver do not belong to this cache")
+    if bool(constant_speed) != bool(equations.have_constant_speed()):
+        raise ValueError("max_dt: constant_speed must be have_constant_speed(equations)")
+    return semi.max_dt(u, t)
+
+
+def calc_error_norms(func, u_ode, t, analyzer, semi, cache_analysis=None):
+    """reference src/semidiscretization/semidiscretization_hyperbolic.jl:97-105 -> analysis_dg_3d.jl:45-89; `func` must
+    be `cons2cons` (the device kernel reduces the conserved variables against the enumerated initial condition)."""
+    if func is not cons2cons:
+        raise NotImplementedError("calc_error_norms on the device is enumerated for cons2cons")
+    mesh, equations, solver, cache = mesh_equations_solver_cache(semi)
+    u = wrap_array(u_ode, mesh, equations, solver, cache)
+    return _need_cache(cache, "calc_error_norms").calc_error_norms(u, t, analyzer)
+
+
+def integrate(func, u, mesh, equations, dg, cache, normalize=True):
+    """reference src/callbacks_step/analysis_dg_3d.jl:35-43 for `func = cons2cons`."""
+    if func is not cons2cons:
+        raise NotImplementedError("integrate on the device is enumerated for cons2cons")
+    return _need_cache(cache, "integrate").integrate(u, normalize=normalize)
+
+
+def cons2cons(u, equations):
+    return u
