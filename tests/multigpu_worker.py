@@ -32,6 +32,9 @@ def main():
         for staged in (False, True):
             comm_id = D.broadcast_comm_id()
             semi = cases.make_semi(c, staged_only=staged, device=local_rank, rank=rank, nranks=world, comm_id=comm_id)
+            if rank == 0:
+                print(f"[multigpu] {name} staged={staged} in-kernel peer-memory halo exchange: "
+                      f"{bool(semi.size('p2p_halo'))}", flush=True)
             lo = semi.local_slice(u)
             u_d = torch.from_numpy(np.ascontiguousarray(lo)).to(semi.device)
             du_d = semi.new_vector().fill_(float("nan"))

@@ -415,3 +415,19 @@ def test_oracle_equals_independent_numpy_restatement_3d_euler_ec():
     l2o, linfo = o.error_norms(uo, e["tend"])
     l2n, linfn = g.error_norms(un, I.weak_blast_wave)
     assert np.abs(l2n - l2o).max() <= 1e-13 and np.abs(linfn - linfo).max() <= 1e-12
+
+
+def test_opcount_of_one_rhs_per_dof():
+    """oracle/opcount_main.cpp (the oracle's headers compiled with an instrumented scalar) reproduces the committed
+    profiles/r2_opcount.json: the flop/DOF figures bench.py's FP64 roofline view uses are counted, not estimated."""
+    import subprocess
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    subprocess.run(["make", "-C", os.path.join(root, "oracle"), "-s", "opcount"], check=True)
+    out = json.loads(subprocess.run([os.path.join(root, "oracle", "_build", "opcount")], check=True,
+                                    capture_output=True, text=True).stdout)
+    ref = json.load(open(os.path.join(root, "profiles", "r2_opcount.json")))
+    for k in ("c1_advection_1d", "c2_euler_ec_2d", "c3_euler_sc_3d", "c4_mhd_alfven_mortar_3d", "c5_euler_ec_3d"):
+        assert abs(out[k]["flop_per_dof"] - ref[k]["flop_per_dof"]) <= 1e-9 * ref[k]["flop_per_dof"], k
+    # 3D Euler EC, p = 3: 4.5 symmetric volume pairs + 0.75 interface fluxes per DOF, ~115 flop per flux_ranocha call
+    # (Trixi's flux converts both states to primitive variables itself) + accumulation
+    assert 550 < out["c5_euler_ec_3d"]["flop_per_dof"] < 700

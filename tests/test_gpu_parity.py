@@ -399,20 +399,31 @@ def test_rhs_host_chunk_pipeline(name, level, monkeypatch):
     assert semi.launch_count() > 3 * 8          # one launch per chunk
 
 
+@pytest.mark.parametrize("halo", ["p2p", "nccl"])
 @pytest.mark.parametrize("nranks", [2, 4, 8])
-def test_multi_gpu_rhs_matches_oracle(nranks):
-    """Morton-curve partition over `nranks` GPUs of this box (one process per GPU, NCCL halo exchange)."""
+def test_multi_gpu_rhs_matches_oracle(nranks, halo):
+    """Morton-curve partition over `nranks` GPUs of this box (one process per GPU). halo = "p2p": the line-owner
+    kernel packs into the peers' mapped buffers and waits on flag words (one launch per rhs!); "nccl": pack kernel +
+    grouped ncclSend/ncclRecv + two launches (TRIXIB200_HALO=nccl; also what the staged / node kernels use)."""
     import subprocess, sys
     torch = _torch()
     if torch.cuda.device_count() < nranks:
         pytest.skip(f"needs {nranks} GPUs")
     here = _os.path.dirname(_os.path.abspath(__file__))
-    port = 29700 + nranks
+    port = 29700 + nranks + (20 if halo == "nccl" else 0)
+    env = dict(_os.environ)
+    if halo == "nccl":
+        env["TRIXIB200_HALO"] = "nccl"
+    else:
+        env.pop("TRIXIB200_HALO", None)
     res = subprocess.run([sys.executable, "-m", "torch.distributed.run", "--nnodes=1", f"--nproc-per-node={nranks}",
                           "--master-addr", "127.0.0.1", "--master-port", str(port),
-                          _os.path.join(here, "multigpu_worker.py")], capture_output=True, text=True, timeout=900)
+                          _os.path.join(here, "multigpu_worker.py")], capture_output=True, text=True, timeout=900,
+                         env=env)
     assert res.returncode == 0, res.stdout[-3000:] + res.stderr[-3000:]
     assert res.stdout.count("MULTIGPU_OK") == nranks, res.stdout[-2000:]
+    used = "in-kernel peer-memory halo exchange: True" in res.stdout
+    assert used == (halo == "p2p"), res.stdout[-2000:]
 
 
 @pytest.mark.parametrize("name", ["c5_euler_ec_3d", "c2_euler_ec_2d", "c1_advection_1d", "advection_basic_3d"])

@@ -120,6 +120,35 @@ struct RkArgs {
   double a, b, dt;
 };
 
+// Halo exchange inside the kernel (multi-GPU, one process per GPU, peers' buffers mapped with CUDA IPC): every CTA
+// first packs its share of the cut-face traces STRAIGHT INTO THE PEERS' receive buffers over NVLink (plain stores to
+// peer memory), the last CTA to finish raises this rank's flag word in every peer's memory to the epoch of this rhs!,
+// then all warps work through the interior elements; a warp looks at its own flag words (written by the peers) only
+// when it reaches the first element pair that touches a cut face. One launch per rhs!, no NCCL kernel, no host-side
+// event between the exchange and the cut elements. The receive buffers are double-buffered by epoch parity: a peer
+// can only start writing epoch e + 2 after it has seen this rank's flag of epoch e + 1, which is raised by a kernel
+// that runs after the one reading epoch e has finished (stream order).
+// No deadlock: packing never waits, so every CTA of every rank raises its share before anybody spins.
+struct P2PArgs {
+  int npeers = 0;                              // 0: no exchange in this launch
+  int first_cut_pair = 0;                      // element pairs >= this index may read halo traces
+  unsigned long long epoch = 0;
+  const int* peer_first = nullptr;             // [npeers + 1] first send slot of every peer (prefix sums)
+  const int* peer_rank = nullptr;              // [npeers]
+  double* const* peer_dst = nullptr;           // [npeers] where this rank's first slot for that peer lands (peer memory)
+  unsigned long long* const* peer_flag = nullptr;   // [npeers] this rank's flag word in the peer's memory
+  const unsigned long long* my_flags = nullptr;     // [nranks] flag words the peers write here
+  unsigned int* done_counter = nullptr;        // CTAs of this launch that have finished packing (reset by the last)
+};
+TB_D unsigned long long l6_ld_acquire_sys(const unsigned long long* p) {
+  unsigned long long v;
+  asm volatile("ld.acquire.sys.global.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
+  return v;
+}
+TB_D void l6_st_release_sys(unsigned long long* p, unsigned long long v) {
+  asm volatile("st.release.sys.global.u64 [%0], %1;" ::"l"(p), "l"(v) : "memory");
+}
+
 // registers per thread that let CTAS CTAs of WARPS warps share the 64 K registers of an SM (allocation unit: 8 per thread)
 constexpr int l6_maxnreg(int warps, int ctas) {
   const int r = (65536 / (32 * warps * ctas)) / 8 * 8;
@@ -134,9 +163,20 @@ constexpr int l6_maxnreg(int warps, int ctas) {
 // accumulated. Every SM sub-partition then holds one warp that feeds the FP64 pipe at its 2-cycle cadence and two warps
 // whose shared-memory / address / copy instructions issue in the gaps, instead of two warps that are in the same kind
 // of section half of the time (profiles/r1_line6_notes.md: 0.68 eligible warps per cycle, FP64 pipe 52 % busy).
+// L6_PP_TOKENS = 1: one warpgroup at a time in its flux part (232 registers there, 136 elsewhere: 232 + 2 * 136 = 504 =
+// 3 * 168). L6_PP_TOKENS = 2: two at a time (192 + 192 + 120 = 504), in rotation order: warpgroup k may enter its n-th
+// flux part when warpgroup (k + 1) % 3 has left its previous one.
+#ifndef L6_PP_TOKENS
+#define L6_PP_TOKENS 1
+#endif
 #ifndef L6_PP_HI
+#if L6_PP_TOKENS == 2
+#define L6_PP_HI 192
+#define L6_PP_LO 120
+#else
 #define L6_PP_HI 232
-#define L6_PP_LO 136     // 232 + 2 * 136 = 504 = 3 * 168
+#define L6_PP_LO 136
+#endif
 #endif
 template <int REGS> TB_D void l6_reg_inc() { asm volatile("setmaxnreg.inc.sync.aligned.u32 %0;\n" ::"n"(REGS)); }
 template <int REGS> TB_D void l6_reg_dec() { asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;\n" ::"n"(REGS)); }
@@ -155,7 +195,7 @@ template <int VFLUX, int SFLUX, bool SFV, int WARPS, int CTAS, int NP, bool RK =
 __global__ void __launch_bounds__(32 * WARPS) __maxnreg__(l6_maxnreg(WARPS, CTAS))
 k_line6(const __grid_constant__ Dev d, const __grid_constant__ LineOps ops, double* __restrict__ du,
         const double* __restrict__ u, double t, const int* __restrict__ elems, int64_t count,
-        const __grid_constant__ RkArgs rk) {
+        const __grid_constant__ RkArgs rk, const __grid_constant__ P2PArgs p2p) {
   // TILE: the x phase parks its 20 doubles per lane in a padded shared tile and a second pass moves whole 16-byte
   // chunks l16 + 16 m, i.e. fully coalesced global accesses. A 16-byte access per lane at a 160-byte stride touches
   // ~40 cache lines per warp instruction and makes the L1 the bottleneck of the fused RK stage (7.6 vs 5.8 ms at
@@ -257,6 +297,47 @@ k_line6(const __grid_constant__ Dev d, const __grid_constant__ LineOps ops, doub
   using D1 = std::integral_constant<int, 1>;
   using D2 = std::integral_constant<int, 2>;
 
+  // ---- multi-GPU: pack the cut-face traces into the peers' receive buffers, then raise the flags (see P2PArgs)
+  bool halo_ready = p2p.npeers == 0;
+  if (p2p.npeers != 0) {
+    const int lane = threadIdx.x & 31;
+    const int nslots = p2p.peer_first[p2p.npeers];
+    for (int sl = wid; sl < nslots; sl += nw) {
+      int k = 0;
+      while (sl >= p2p.peer_first[k + 1]) ++k;
+      double* dst = p2p.peer_dst[k] + (size_t)(sl - p2p.peer_first[k]) * (16 * NV);
+      const int se = d.send_elem[sl], sdir = d.send_dir[sl];
+      const double* ue = u + (size_t)NV * NN * se;
+      const int fixed = (sdir & 1) ? 3 : 0, sdim = sdir >> 1;
+#pragma unroll
+      for (int it2 = 0; it2 < 3; ++it2) {
+        const int i = lane + 32 * it2;
+        if (i < 16 * NV) {
+          const int f = i / NV, v = i - NV * f;
+          dst[i] = ue[NV * face_node<3>(4, sdim, fixed, f) + v];      // layout [f][v] like k_pack_halo
+        }
+      }
+    }
+    __threadfence_system();
+    __syncthreads();
+    if (threadIdx.x == 0) {
+      const unsigned old = atomicAdd(p2p.done_counter, 1u);
+      if (old == gridDim.x - 1) {                      // every CTA of this launch has packed and fenced
+        *p2p.done_counter = 0;                         // the next launch is ordered behind this one
+        __threadfence_system();
+        for (int k = 0; k < p2p.npeers; ++k) l6_st_release_sys(p2p.peer_flag[k], p2p.epoch);
+      }
+    }
+  }
+  // a warp calls this before it touches the first halo trace (prefetch of a pair >= first_cut_pair)
+  auto wait_halo = [&]() {
+    if (!halo_ready) {
+      for (int k = (int)(threadIdx.x & 31); k < p2p.npeers; k += 32)
+        while (l6_ld_acquire_sys(p2p.my_flags + p2p.peer_rank[k]) < p2p.epoch) {}
+      __syncwarp();
+      halo_ready = true;
+    }
+  };
   static_assert(!PP || (WARPS == 12 && CTAS == 1 && NP >= 4), "ping-pong shape: 3 warpgroups, one CTA per SM");
   // PP: every warp of the CTA runs the same number of iterations (the token goes round the three warpgroups in a fixed
   // order); warps whose pair index runs past the end repeat the last element with their stores switched off
@@ -264,7 +345,10 @@ k_line6(const __grid_constant__ Dev d, const __grid_constant__ LineOps ops, doub
   const int niter = PP ? (npairs + nw - 1) / nw : 0;
   if (PP) {
     l6_reg_dec<L6_PP_LO>();
-    if (wg == 2) l6_bar_arrive(1, 256);       // the first token goes to warpgroup 0
+    // barrier 1 + k lets warpgroup k into its flux part; it is raised by warpgroup (k + 3 - TOKENS) % 3 when that one
+    // leaves a flux part, and once at the start for the first TOKENS warpgroups
+    for (int k = 0; k < L6_PP_TOKENS; ++k)
+      if (wg == (k + 3 - L6_PP_TOKENS) % 3) l6_bar_arrive(1 + k, 256);
   }
   unsigned fbits = 0;
   int pr = wid;
@@ -274,6 +358,7 @@ k_line6(const __grid_constant__ Dev d, const __grid_constant__ LineOps ops, doub
   // of an iteration only the x-traces may be pending (wait_group 1), at the x phase the z- and y-traces of the next
   // pair (wait_group 2)
   if (PP || pr < npairs) {
+    if (pr >= p2p.first_cut_pair) wait_halo();
     e = elem_of(pr, valid);
     const int2 cx = load_codes(e, 0), cy = load_codes(e, 1), cz = load_codes(e, 2);
     fbits = face_bits(cx, 0) | face_bits(cy, 1) | face_bits(cz, 2);
@@ -483,8 +568,8 @@ k_line6(const __grid_constant__ Dev d, const __grid_constant__ LineOps ops, doub
           for (int v = 0; v < NV; ++v) accumulate(k, v);
           // PP: the next warpgroup is woken a little before this one gives its registers back, so that its wake-up
           // latency is hidden behind the last accumulations
-          if (PP && K0 + k == L6_PP_ARRIVE_K)
-            l6_bar_arrive_after(wg == 2 ? 1 : 2 + wg, 256, acc[L6_PB[K0 + k] - 1 > 3 ? 3 : L6_PB[K0 + k] - 1][NV - 1]);
+          if (PP && L6_PP_TOKENS == 1 && K0 + k == L6_PP_ARRIVE_K)
+            l6_bar_arrive_after(1 + (wg + L6_PP_TOKENS) % 3, 256, acc[L6_PB[K0 + k] - 1 > 3 ? 3 : L6_PB[K0 + k] - 1][NV - 1]);
         }
         if (FAST && worst >= L6_ROUGH_HI) {
 #pragma unroll
@@ -510,8 +595,13 @@ k_line6(const __grid_constant__ Dev d, const __grid_constant__ LineOps ops, doub
         if (PP && K0 + NP > 7) {
           // the 8 fluxes are accumulated: registers and token go to the next warpgroup (warpgroup 0
           // absorbs the last one behind the loop)
-          if (L6_PP_ARRIVE_K >= 8) l6_bar_arrive(wg == 2 ? 1 : 2 + wg, 256);
+#if L6_PP_TOKENS == 1
+          if (L6_PP_ARRIVE_K >= 8) l6_bar_arrive(1 + (wg + L6_PP_TOKENS) % 3, 256);
           l6_reg_dec<L6_PP_LO>();
+#else
+          l6_reg_dec<L6_PP_LO>();        // with two tokens the registers must be back before the next one is let in
+          l6_bar_arrive(1 + (wg + L6_PP_TOKENS) % 3, 256);
+#endif
           relane();
           repos();
         }
@@ -605,6 +695,7 @@ k_line6(const __grid_constant__ Dev d, const __grid_constant__ LineOps ops, doub
         }
       }
       __syncwarp();   // traces consumed, running sums visible
+      if (pr_next >= p2p.first_cut_pair) wait_halo();
       if (dir == 0) issue_traces(D0{}, e_next, cn.x, cn.y);
       else if (dir == 1) issue_traces(D1{}, e_next, cn.x, cn.y);
       else issue_traces(D2{}, e_next, cn.x, cn.y);
@@ -614,7 +705,7 @@ k_line6(const __grid_constant__ Dev d, const __grid_constant__ LineOps ops, doub
     e = e_next; valid = valid_next; fbits = fbits_next;
   }
   cp_async_wait<0>();
-  if (PP && wg == 0) l6_bar_sync(1, 256);   // takes the token warpgroup 2 passed on after the CTA's last flux part
+  if (PP && wg < L6_PP_TOKENS) l6_bar_sync(1 + wg, 256);   // takes the token that was passed on after the CTA's last flux parts
 }
 
 // ---------------------------------------------------------------------------------------------- host side
@@ -626,7 +717,8 @@ k_line6(const __grid_constant__ Dev d, const __grid_constant__ LineOps ops, doub
 template <int VFLUX, int SFLUX, bool SFV, int CTAS, int WARPS, int NP, bool RK = false, bool TOUT = false,
           bool PP = false>
 static int line6_launch_t(const Dev& d, const LineOps& ops, double* du, const double* u, double t, const int* elems,
-                          int64_t count, cudaStream_t stream, int sm_count, const RkArgs& rk = RkArgs{nullptr, 0, 0, 0}) {
+                          int64_t count, cudaStream_t stream, int sm_count, const RkArgs& rk = RkArgs{nullptr, 0, 0, 0},
+                          const P2PArgs& p2p = P2PArgs{}) {
   auto kern = k_line6<VFLUX, SFLUX, SFV, WARPS, CTAS, NP, RK, TOUT, PP>;
   static DeviceOnce configured;
   if (configured.need()) {
@@ -638,40 +730,43 @@ static int line6_launch_t(const Dev& d, const LineOps& ops, double* du, const do
   const int64_t npairs = (count + 1) / 2;
   const int64_t want = (npairs + WARPS - 1) / WARPS;
   const unsigned blocks = (unsigned)std::min<int64_t>(want, (int64_t)sm_count * CTAS);
-  kern<<<blocks, 32 * WARPS, l6_smem(WARPS), stream>>>(d, ops, du, u, t, elems, count, rk);
+  kern<<<blocks, 32 * WARPS, l6_smem(WARPS), stream>>>(d, ops, du, u, t, elems, count, rk, p2p);
   return cudaGetLastError() == cudaSuccess ? 0 : TRIXIB200_ECUDA;
 }
 
 static int line6_launch(const trixib200_config& c, const Dev& d, const LineOps& ops, double* du, const double* u,
-                        double t, const int* elems, int64_t count, cudaStream_t s, int sm_count) {
+                        double t, const int* elems, int64_t count, cudaStream_t s, int sm_count,
+                        const P2PArgs& p2p = P2PArgs{}) {
+  const RkArgs rk{nullptr, 0, 0, 0};
   constexpr int R = TRIXIB200_FLUX_RANOCHA;
   const bool sfv = d.B > 0 || d.M > 0;   // faces whose flux is given in surface_flux_values (boundaries, mortars)
   if (c.volume_flux == R && c.surface_flux == R) {
     // TRIXIB200_LINE_SHAPE=3: 3 CTAs x 4 warps per SM at 168 registers, batches of 2 pairs (A/B measurements)
     static const bool three = getenv("TRIXIB200_LINE_SHAPE") && atoi(getenv("TRIXIB200_LINE_SHAPE")) == 3;
-    if (three && !sfv) return line6_launch_t<R, R, false, 3, 4, 2>(d, ops, du, u, t, elems, count, s, sm_count);
+    if (three && !sfv) return line6_launch_t<R, R, false, 3, 4, 2>(d, ops, du, u, t, elems, count, s, sm_count, rk, p2p);
     // TRIXIB200_LINE_SHAPE=8: du stored directly from the x-line owners (160-byte runs per lane) instead of through
     // the shared tile (A/B measurements: 4.71 vs 4.66 ms at level 7)
     static const bool direct = getenv("TRIXIB200_LINE_SHAPE") && atoi(getenv("TRIXIB200_LINE_SHAPE")) == 8;
-    if (direct && !sfv) return line6_launch_t<R, R, false, 2, 4, 8>(d, ops, du, u, t, elems, count, s, sm_count);
+    if (direct && !sfv) return line6_launch_t<R, R, false, 2, 4, 8>(d, ops, du, u, t, elems, count, s, sm_count, rk, p2p);
     // TRIXIB200_LINE_SHAPE=12: the ping-pong shape (3 warpgroups, flux parts serialised by a token, setmaxnreg)
     static const bool pp = getenv("TRIXIB200_LINE_SHAPE") && atoi(getenv("TRIXIB200_LINE_SHAPE")) == 12;
-    if (pp && !sfv) return line6_launch_t<R, R, false, 1, 12, 8, false, true, true>(d, ops, du, u, t, elems, count, s, sm_count);
+    if (pp && !sfv) return line6_launch_t<R, R, false, 1, 12, 8, false, true, true>(d, ops, du, u, t, elems, count, s, sm_count, rk, p2p);
     return sfv ? line6_launch_t<R, R, true, 2, 4, 8, false, true>(d, ops, du, u, t, elems, count, s, sm_count)
-               : line6_launch_t<R, R, false, 2, 4, 8, false, true>(d, ops, du, u, t, elems, count, s, sm_count);
+               : line6_launch_t<R, R, false, 2, 4, 8, false, true>(d, ops, du, u, t, elems, count, s, sm_count, rk, p2p);
   }
-  return line6_launch_t<-1, -1, true, 2, 4, 2, false, true>(d, ops, du, u, t, elems, count, s, sm_count);
+  return line6_launch_t<-1, -1, true, 2, 4, 2, false, true>(d, ops, du, u, t, elems, count, s, sm_count, rk, p2p);
 }
 
 // rhs! fused with the 2N Runge-Kutta stage update: u_out = u_in + b * (tmp = a * tmp + dt * rhs(u_in, t))
 static int line6_launch_rk(const trixib200_config& c, const Dev& d, const LineOps& ops, double* u_out, const double* u_in,
-                           double t, const int* elems, int64_t count, cudaStream_t s, int sm_count, const RkArgs& rk) {
+                           double t, const int* elems, int64_t count, cudaStream_t s, int sm_count, const RkArgs& rk,
+                           const P2PArgs& p2p = P2PArgs{}) {
   constexpr int R = TRIXIB200_FLUX_RANOCHA;
   const bool sfv = d.B > 0 || d.M > 0;
   if (c.volume_flux == R && c.surface_flux == R)
     return sfv ? line6_launch_t<R, R, true, 2, 4, 8, true>(d, ops, u_out, u_in, t, elems, count, s, sm_count, rk)
-               : line6_launch_t<R, R, false, 2, 4, 8, true>(d, ops, u_out, u_in, t, elems, count, s, sm_count, rk);
-  return line6_launch_t<-1, -1, true, 2, 4, 2, true>(d, ops, u_out, u_in, t, elems, count, s, sm_count, rk);
+               : line6_launch_t<R, R, false, 2, 4, 8, true>(d, ops, u_out, u_in, t, elems, count, s, sm_count, rk, p2p);
+  return line6_launch_t<-1, -1, true, 2, 4, 2, true>(d, ops, u_out, u_in, t, elems, count, s, sm_count, rk, p2p);
 }
 
 }  // namespace tb

@@ -43,6 +43,7 @@ struct Nccl {
   int (*Send)(const void*, size_t, int, int, ncclComm_t, cudaStream_t) = nullptr;
   int (*Recv)(void*, size_t, int, int, ncclComm_t, cudaStream_t) = nullptr;
   int (*AllReduce)(const void*, void*, size_t, int, int, ncclComm_t, cudaStream_t) = nullptr;
+  int (*AllGather)(const void*, void*, size_t, int, ncclComm_t, cudaStream_t) = nullptr;
   int (*GroupStart)() = nullptr;
   int (*GroupEnd)() = nullptr;
   const char* (*GetErrorString)(int) = nullptr;
@@ -54,7 +55,7 @@ struct Nccl {
     if (!lib) lib = dlopen("libnccl.so", RTLD_NOW);
     if (!lib) return false;
 #define SYM(n) *(void**)(&n) = dlsym(lib, "nccl" #n)
-    SYM(GetUniqueId); SYM(CommInitRank); SYM(CommDestroy); SYM(Send); SYM(Recv); SYM(AllReduce);
+    SYM(GetUniqueId); SYM(CommInitRank); SYM(CommDestroy); SYM(Send); SYM(Recv); SYM(AllReduce); SYM(AllGather);
     SYM(GroupStart); SYM(GroupEnd); SYM(GetErrorString);
 #undef SYM
     return GetUniqueId && CommInitRank && Send && Recv && AllReduce && GroupStart && GroupEnd;
@@ -62,6 +63,7 @@ struct Nccl {
 };
 static Nccl g_nccl;
 constexpr int NCCL_FLOAT64 = 8, NCCL_SUM = 0, NCCL_MAX = 2;
+constexpr size_t P2P_FLAG_BYTES = 512;    // in-kernel halo exchange: 64 flag words, rank r raises word r in its peers' memory
 
 
 // ---------------------------------------------------------------------------------------------- partition plan
@@ -248,6 +250,22 @@ struct trixib200_handle {
   std::vector<int64_t> peer_count;        // faces exchanged with each peer (send == recv count)
   ncclComm_t comm = nullptr;
   int sm_count = 148;
+  // in-kernel halo exchange over peer memory (CUDA IPC; see P2PArgs in kernels_line6.cuh)
+  struct P2P {
+    bool enabled = false;
+    bool mesh_ok = false;                      // no boundary / mortar faces anywhere in the GLOBAL mesh (same on all ranks)
+    std::string why = "not set up";            // why it is off (reported by trixib200_last_error after size("p2p_halo"))
+    unsigned char* base = nullptr;             // local: [flags P2P_FLAG_BYTES][recv buffer epoch-parity 0][parity 1]
+    size_t buf_doubles = 0;
+    unsigned long long epoch = 0;
+    std::vector<void*> peer_base;              // opened IPC mappings of the peers' allocations
+    int* d_peer_first = nullptr; int* d_peer_rank = nullptr;
+    double** d_peer_dst[2] = {nullptr, nullptr};
+    unsigned long long** d_peer_flag = nullptr;
+    unsigned int* d_done = nullptr;
+    int* d_elems_all = nullptr;                // interior elements, then the elements that touch a cut face
+    std::vector<int64_t> slot_off;             // [nranks] first halo slot of every peer rank (-1: not a peer)
+  } p2p;
   // rhs_host: library-owned device mirrors of the caller's host vectors, and the chunk pipeline
   double* host_u = nullptr; double* host_du = nullptr;
   double* an_buf = nullptr;                // analysis kernels: operators + per-CTA partials (lazy)
@@ -341,6 +359,8 @@ extern "C" int trixib200_destroy(trixib200_handle* h) {
   if (!h) return 0;
   cudaSetDevice(h->cfg.device);
   if (h->stream) cudaStreamSynchronize(h->stream);
+  for (void* pb : h->p2p.peer_base) if (pb) cudaIpcCloseMemHandle(pb);
+  if (h->p2p.base) cudaFree(h->p2p.base);
   if (h->comm && g_nccl.CommDestroy) g_nccl.CommDestroy(h->comm);
   for (void* p : h->allocs) cudaFree(p);
   if (h->ev_pack) cudaEventDestroy(h->ev_pack);
@@ -546,6 +566,13 @@ static int create_impl(const trixib200_config* cfg, const trixib200_basis_host* 
     h->n_interior = (int64_t)P.elems_interior.size(); h->n_halo_elems = (int64_t)P.elems_halo.size();
     if (int rc = upload(h, P.elems_interior, &p)) return rc; h->d_elems_interior = p;
     if (int rc = upload(h, P.elems_halo, &p)) return rc; h->d_elems_halo = p;
+    std::vector<int> all(P.elems_interior);
+    all.insert(all.end(), P.elems_halo.begin(), P.elems_halo.end());
+    if (int rc = upload(h, all, &p)) return rc; h->p2p.d_elems_all = p;
+    h->p2p.mesh_ok = ms->nboundaries == 0 && ms->nmortars == 0;
+    h->p2p.slot_off.assign(c.nranks, -1);
+    int64_t off = 0;
+    for (size_t k = 0; k < P.peers.size(); ++k) { h->p2p.slot_off[P.peers[k]] = off; off += P.peer_count[k]; }
   }
 
   // ---- materialised containers: the staged path needs all of them; the fused path only what boundary /
@@ -581,6 +608,7 @@ extern "C" int64_t trixib200_size(const trixib200_handle* h, const char* name) {
   std::string n(name);
   const Dev& d = h->d;
   if (n == "nelements") return d.E;
+  if (n == "p2p_halo") { g_err = h->p2p.why; return h->p2p.enabled ? 1 : 0; }
   if (n == "nelements_global") return h->E_global;
   if (n == "first_element") return h->first;
   if (n == "nvars") return d.nv;
@@ -748,12 +776,19 @@ static bool rk_fusable(const trixib200_handle* h, const double* u_out, const dou
 }
 
 static int fused_launch_any(trixib200_handle* h, double* du, const double* u, double t, const int* elems, int64_t count,
-                            const RkArgs* rk = nullptr) {
+                            const RkArgs* rk = nullptr, const P2PArgs* p2p = nullptr, const Dev* dev = nullptr) {
   if (count <= 0) return 0;
-  Dev& d = h->d;
+  const Dev& d = dev ? *dev : h->d;
   if (rk) {   // caller checked rk_fusable(): du is u_out here
-    if (int rc = line6_launch_rk(h->cfg, d, h->line_ops, du, u, t, elems, count, h->stream, h->sm_count, *rk))
+    if (int rc = line6_launch_rk(h->cfg, d, h->line_ops, du, u, t, elems, count, h->stream, h->sm_count, *rk,
+                                 p2p ? *p2p : P2PArgs{}))
       return fail(rc, "fused RK launch failed");
+    h->launches++;
+    return 0;
+  }
+  if (p2p) {  // caller checked that the line-owner kernel takes these vectors
+    if (int rc = line6_launch(h->cfg, d, h->line_ops, du, u, t, elems, count, h->stream, h->sm_count, *p2p))
+      return fail(rc, "fused launch failed");
     h->launches++;
     return 0;
   }
@@ -785,6 +820,27 @@ static int rhs_fused(trixib200_handle* h, double* du, const double* u, double t,
     if (!g_trace.made) { for (auto& e : g_trace.e) cudaEventCreate(&e); g_trace.made = true; }
     cudaDeviceSynchronize();
     cudaEventRecord(g_trace.e[0], h->stream);
+  }
+  // multi-GPU on the line-owner path with mapped peer buffers: ONE launch packs, exchanges and computes
+  // (the decision must be the same on every rank: it only uses global facts)
+  if (h->p2p.enabled && h->cfg.nranks > 1 && h->p2p.mesh_ok) {
+    if ((((uintptr_t)u) | ((uintptr_t)du) | (rk ? (uintptr_t)rk->tmp : 0)) & 15)
+      return fail(TRIXIB200_EINVAL, "multi-GPU rhs!: vectors must be 16-byte aligned");
+    if (line_gen5()) return fail(TRIXIB200_EUNSUPPORTED, "TRIXIB200_LINE_KERNEL=5 has no in-kernel halo exchange");
+    auto& P = h->p2p;
+    const unsigned long long epoch = ++P.epoch;
+    const int par = (int)(epoch & 1);
+    Dev dl = d;
+    dl.halo_recv = (const double*)(P.base + P2P_FLAG_BYTES) + (size_t)par * P.buf_doubles;
+    P2PArgs a;
+    a.npeers = (int)h->peers.size();
+    a.first_cut_pair = (int)(h->n_interior / 2);
+    a.epoch = epoch;
+    a.peer_first = P.d_peer_first; a.peer_rank = P.d_peer_rank;
+    a.peer_dst = P.d_peer_dst[par]; a.peer_flag = P.d_peer_flag;
+    a.my_flags = (const unsigned long long*)P.base;
+    a.done_counter = P.d_done;
+    return fused_launch_any(h, du, u, t, P.d_elems_all, d.E, rk, &a, &dl);
   }
   if (int rc = halo_begin(h, u)) return rc;
   if (tracing) { cudaEventRecord(g_trace.e[1], h->stream); cudaEventRecord(g_trace.e[5], h->comm_stream); }
@@ -1275,6 +1331,111 @@ extern "C" int trixib200_comm_unique_id(char* id128) {
   std::memcpy(id128, id.internal, 128);
   return 0;
 }
+// In-kernel halo exchange: map every peer's receive buffer + flag words with CUDA IPC (one process per GPU, one box).
+// All ranks take the same decision (two collective agreements); on any failure the NCCL send/recv path stays.
+struct P2PRecord {
+  cudaIpcMemHandle_t handle;
+  int64_t ok, nhalo;
+  int64_t slot_off[32];                   // first halo slot of rank r in THIS rank's receive buffer (-1: not a peer)
+};
+static int p2p_agree(trixib200_handle* h, bool mine, bool* all) {
+  double v = mine ? 0.0 : 1.0, out = 0;   // max over ranks of "failed"
+  CUDA_TRY(cudaMemcpyAsync(h->d_scalar, &v, sizeof(double), cudaMemcpyHostToDevice, h->stream));
+  if (g_nccl.AllReduce(h->d_scalar, h->d_scalar, 1, NCCL_FLOAT64, NCCL_MAX, h->comm, h->stream) != 0)
+    return fail(TRIXIB200_ECOMM, "ncclAllReduce failed (p2p agreement)");
+  CUDA_TRY(cudaMemcpyAsync(&out, h->d_scalar, sizeof(double), cudaMemcpyDeviceToHost, h->stream));
+  CUDA_TRY(cudaStreamSynchronize(h->stream));
+  *all = out == 0.0;
+  return 0;
+}
+static int p2p_setup(trixib200_handle* h) {
+  auto& P = h->p2p;
+  Dev& d = h->d;
+  const int nr = h->cfg.nranks, me = h->cfg.rank;
+  const size_t per = (size_t)d.nv * d.nf;
+  const char* env = getenv("TRIXIB200_HALO");
+  bool ok = true;
+  if (env && std::string(env) == "nccl") { ok = false; P.why = "TRIXIB200_HALO=nccl"; }
+  else if (!(h->fused && h->line3d)) { ok = false; P.why = "only the line-owner kernel path packs in-kernel"; }
+  else if (!P.mesh_ok) { ok = false; P.why = "meshes with boundary or mortar faces exchange through NCCL send/recv"; }
+  else if (nr > 32) { ok = false; P.why = "more than 32 ranks"; }
+  else if (!g_nccl.AllGather) { ok = false; P.why = "ncclAllGather not found"; }
+  P2PRecord mine;
+  std::memset(&mine, 0, sizeof(mine));
+  if (ok) {
+    P.buf_doubles = std::max<size_t>(per * (size_t)d.nhalo_recv, 1);
+    const size_t bytes = P2P_FLAG_BYTES + 2 * P.buf_doubles * sizeof(double);
+    if (cudaMalloc((void**)&P.base, bytes) != cudaSuccess || cudaMemset(P.base, 0, bytes) != cudaSuccess ||
+        cudaIpcGetMemHandle(&mine.handle, P.base) != cudaSuccess) {
+      cudaGetLastError();
+      ok = false; P.why = "cudaMalloc / cudaIpcGetMemHandle failed";
+    }
+  }
+  mine.ok = ok ? 1 : 0;
+  mine.nhalo = d.nhalo_recv;
+  for (int r = 0; r < 32; ++r) mine.slot_off[r] = r < nr ? P.slot_off[r] : -1;
+  // every rank's record to every rank
+  std::vector<P2PRecord> recs(nr);
+  {
+    unsigned char* dbuf = nullptr;
+    CUDA_TRY(cudaMalloc((void**)&dbuf, sizeof(P2PRecord) * nr));
+    CUDA_TRY(cudaMemcpyAsync(dbuf + sizeof(P2PRecord) * me, &mine, sizeof(P2PRecord), cudaMemcpyHostToDevice, h->stream));
+    int rc = g_nccl.AllGather ? g_nccl.AllGather(dbuf + sizeof(P2PRecord) * me, dbuf, sizeof(P2PRecord), /*ncclChar*/ 0,
+                                                 h->comm, h->stream) : -1;
+    if (rc == 0) {
+      CUDA_TRY(cudaMemcpyAsync(recs.data(), dbuf, sizeof(P2PRecord) * nr, cudaMemcpyDeviceToHost, h->stream));
+      CUDA_TRY(cudaStreamSynchronize(h->stream));
+    }
+    cudaFree(dbuf);
+    if (rc != 0) { P.why = "ncclAllGather failed"; return 0; }    // collective failed everywhere alike: stay on NCCL p2p
+  }
+  for (int r = 0; r < nr; ++r)
+    if (!recs[r].ok) { if (ok) P.why = "a peer rank could not set up the in-kernel halo exchange"; ok = false; }
+  // open the peers' allocations
+  const size_t np = h->peers.size();
+  std::vector<double*> dst[2];
+  std::vector<unsigned long long*> flag;
+  if (ok) {
+    P.peer_base.assign(np, nullptr);
+    for (size_t k = 0; k < np && ok; ++k) {
+      const int pr = h->peers[k];
+      if (recs[pr].slot_off[me] < 0) { ok = false; P.why = "peer tables disagree"; break; }
+      void* pb = nullptr;
+      if (cudaIpcOpenMemHandle(&pb, recs[pr].handle, cudaIpcMemLazyEnablePeerAccess) != cudaSuccess) {
+        cudaGetLastError();
+        ok = false; P.why = "cudaIpcOpenMemHandle failed (no peer access between these GPUs?)";
+        break;
+      }
+      P.peer_base[k] = pb;
+      const size_t rbuf = std::max<size_t>(per * (size_t)recs[pr].nhalo, 1);
+      double* b0 = (double*)((unsigned char*)pb + P2P_FLAG_BYTES);
+      dst[0].push_back(b0 + per * (size_t)recs[pr].slot_off[me]);
+      dst[1].push_back(b0 + rbuf + per * (size_t)recs[pr].slot_off[me]);
+      flag.push_back((unsigned long long*)pb + me);
+    }
+  }
+  bool all = false;
+  if (int rc = p2p_agree(h, ok, &all)) return rc;
+  if (!all) {
+    if (ok) P.why = "a peer rank could not map the buffers";
+    for (void*& pb : P.peer_base) if (pb) { cudaIpcCloseMemHandle(pb); pb = nullptr; }
+    P.peer_base.clear();
+    return 0;
+  }
+  std::vector<int> first(np + 1, 0), ranks(np, 0);
+  for (size_t k = 0; k < np; ++k) { first[k + 1] = first[k] + (int)h->peer_count[k]; ranks[k] = h->peers[k]; }
+  if (int rc = upload(h, first, &P.d_peer_first)) return rc;
+  if (int rc = upload(h, ranks, &P.d_peer_rank)) return rc;
+  if (int rc = upload(h, dst[0], &P.d_peer_dst[0])) return rc;
+  if (int rc = upload(h, dst[1], &P.d_peer_dst[1])) return rc;
+  if (int rc = upload(h, flag, &P.d_peer_flag)) return rc;
+  std::vector<unsigned int> zero(1, 0u);
+  if (int rc = upload(h, zero, &P.d_done)) return rc;
+  P.enabled = true;
+  P.why = "";
+  return 0;
+}
+
 extern "C" int trixib200_comm_init(trixib200_handle* h, const char* id128) {
   if (!h || !id128) return fail(TRIXIB200_EINVAL, "null argument");
   if (h->cfg.nranks == 1) return 0;
@@ -1284,5 +1445,5 @@ extern "C" int trixib200_comm_init(trixib200_handle* h, const char* id128) {
   std::memcpy(id.internal, id128, 128);
   int rc = g_nccl.CommInitRank(&h->comm, h->cfg.nranks, id, h->cfg.rank);
   if (rc != 0) return fail(TRIXIB200_ECOMM, std::string("ncclCommInitRank: ") + (g_nccl.GetErrorString ? g_nccl.GetErrorString(rc) : "?"));
-  return 0;
+  return p2p_setup(h);
 }
