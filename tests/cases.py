@@ -7,6 +7,8 @@ import oracle as O
 
 BOX3 = (dict(type="box", coordinates_min=(-0.5, -0.5, -0.5), coordinates_max=(0.5, 0.5, 0.5)),)
 BOX2 = (dict(type="box", coordinates_min=(0.0, -1.0), coordinates_max=(1.0, 1.0)),)
+# a patch whose mortars are cut by the Morton-range partition at 2, 4 and 8 ranks (7 / 11 / 15 of its 24 mortars)
+BOX3_OFF = (dict(type="box", coordinates_min=(-0.5, -0.5, -1.0), coordinates_max=(0.5, 0.5, 0.0)),)
 
 
 def case(ndim, equations, level=2, polydeg=3, vi="weak_form", volume_flux="flux_central",
@@ -82,6 +84,14 @@ CASES = {
                                cmin=-2.0, cmax=2.0),
     "euler_slip_wall_2d": case(2, "euler", level=3, surface_flux="flux_hll", ic="weak_blast_wave", bc="slip_wall",
                                periodic=False, cmin=-2.0, cmax=2.0),
+    # mortars that cross partition cuts (multi-GPU: replicated on every rank that owns one of their elements)
+    "euler_ec_mortar_off_3d": case(3, "euler", level=2, vi="flux_differencing", volume_flux="flux_ranocha",
+                                   surface_flux="flux_ranocha", ic="weak_blast_wave", patches=BOX3_OFF),
+    "mhd_alfven_mortar_off_3d": case(3, "mhd", level=2, vi="flux_differencing", volume_flux="flux_hindenlang_gassner",
+                                     surface_flux="flux_hlle", noncons=True, gamma=5 / 3, patches=BOX3_OFF, c_h=1.3),
+    "euler_shock_mortar_off_3d": case(3, "euler", level=2, vi="shock_capturing_hg", volume_flux="flux_ranocha",
+                                      volume_flux_fv="flux_lax_friedrichs", surface_flux="flux_lax_friedrichs",
+                                      ic="weak_blast_wave", patches=BOX3_OFF),
     # other polynomial degrees go through the staged kernels
     "euler_ec_3d_p2": case(3, "euler", level=2, polydeg=2, vi="flux_differencing", volume_flux="flux_ranocha",
                            surface_flux="flux_ranocha", ic="weak_blast_wave", cmin=-2.0, cmax=2.0),

@@ -18,9 +18,14 @@ import cases  # noqa: E402
 def main():
     from trixib200 import distributed as D
     rank, local_rank, world = D.init_process_group(backend="nccl")
-    for name, level in (("c5_euler_ec_3d", 3), ("c2_euler_ec_2d", 4), ("euler_source_terms_3d", 2),
+    lv = int(os.environ.get("TRIXIB200_MULTI_LEVEL", "3"))     # level of the line-kernel case (4-5 for the 8-rank log)
+    for name, level in (("c5_euler_ec_3d", lv), ("c2_euler_ec_2d", 4), ("euler_source_terms_3d", 2),
                         ("euler_nonperiodic_3d", 2), ("advection_basic_3d", 3), ("mhd_ec_3d", 2),
-                        ("c3_euler_sc_3d_nosmooth", 3)):
+                        ("c3_euler_sc_3d_nosmooth", 3),
+                        # alpha smoothing across cuts, mortars replicated across cuts
+                        ("c3_euler_sc_3d", 3), ("c4_mhd_alfven_mortar_3d", 2), ("euler_ec_mortar_off_3d", 2),
+                        ("mhd_alfven_mortar_off_3d", 2), ("euler_shock_mortar_off_3d", 2), ("euler_ec_mortar_2d", 3),
+                        ("euler_shock_2d", 4)):
         if name == "c3_euler_sc_3d_nosmooth":
             c = dict(cases.CASES["c3_euler_sc_3d"], alpha_smooth=False, level=level)
         else:

@@ -129,13 +129,14 @@ def test_partition_plan_invariants(name, nranks):
             if R[s] >= 0:
                 assert fn[R[s], 2 * dim[s]] == L[s]
         # send list: peer-major, same global interfaces in the same order on both sides
-        peers, cnt = p.array("peers"), p.array("peer_count")
+        peers, cnt, scnt = p.array("peers"), p.array("peer_count"), p.array("peer_send_count")
+        assert np.array_equal(cnt, scnt)            # no mortars: one face received per face sent
         sg = p.array("send_global_iface")
         off = 0
-        for q, k in zip(peers, cnt):
+        for q, k in zip(peers, scnt):
             mine = sg[off: off + k]
             pq = plans[q]
-            qpeers, qcnt, qsg = pq.array("peers"), pq.array("peer_count"), pq.array("send_global_iface")
+            qpeers, qcnt, qsg = pq.array("peers"), pq.array("peer_send_count"), pq.array("send_global_iface")
             qoff = int(sum(qcnt[: list(qpeers).index(r)]))
             assert np.array_equal(mine, qsg[qoff: qoff + k])
             off += k
@@ -145,11 +146,79 @@ def test_partition_plan_invariants(name, nranks):
     assert seen.min() >= 1 and seen.max() <= 2
 
 
-def test_partition_rejects_mortar_across_ranks_and_bad_args():
+@pytest.mark.parametrize("nranks", [2, 3, 4, 8])
+@pytest.mark.parametrize("name", ["box_3d", "box_2d"])
+def test_partition_plan_replicates_cut_mortars(name, nranks):
+    """A mortar whose elements live on several ranks exists on every one of them: rows of
+    elements the rank does not own are halo codes, and delivering every rank's send list to its peers in peer order
+    puts exactly the face (global element, direction) into the slot each halo code names -- for cut interfaces and
+    for the replicated mortars alike."""
+    mesh, basis, c, _ = _build(MESHES[name])
+    nd = mesh.ndim
+    rows = (4 if nd == 3 else 2) + 1
+    plans = [_plan(mesh, basis, r, nranks)[0] for r in range(nranks)]
+    firsts = [p.scalar("first_element") for p in plans]
+    counts = [p.scalar("nelements") for p in plans]
+    owner = np.concatenate([np.full(n, r) for r, n in enumerate(counts)])
+    mo_gl = c.mortars.neighbor_ids - 1                        # [rows, M] global 0-based
+    # deliver: recv[q][slot] = (global element, direction) of the face that lands there
+    recv = [dict() for _ in range(nranks)]
+    for r, p in enumerate(plans):
+        peers, scnt = p.array("peers"), p.array("peer_send_count")
+        se, sd = p.array("send_elem"), p.array("send_dir")
+        off = 0
+        for q, k in zip(peers, scnt):
+            pq = plans[q]
+            qpeers, qrcnt = list(pq.array("peers")), pq.array("peer_count")
+            assert r in qpeers and qrcnt[qpeers.index(r)] == k         # what r sends to q is what q expects from r
+            qoff = int(sum(qrcnt[: qpeers.index(r)]))
+            for i in range(k):
+                recv[q][qoff + i] = (int(se[off + i]) + firsts[r], int(sd[off + i]))
+            off += k
+    n_replicas = np.zeros(mo_gl.shape[1], dtype=int)
+    for r, p in enumerate(plans):
+        assert len(recv[r]) == int(p.array("peer_count").sum())           # every slot is written exactly once
+        ids = p.array("mo_ids").reshape(-1, rows)
+        mg, side, dim = p.array("mo_global"), p.array("mo_side"), p.array("mo_dim")
+        # exactly the mortars with at least one local element, in global order
+        want = [m for m in range(mo_gl.shape[1]) if (owner[mo_gl[:, m]] == r).any()]
+        assert list(mg) == want
+        for ml, m in enumerate(mg):
+            n_replicas[m] += 1
+            o1, ls = dim[ml] + 1, side[ml]
+            assert o1 == c.mortars.orientations[m] and ls == c.mortars.large_sides[m]
+            for row in range(rows):
+                g = mo_gl[row, m]
+                want_dir = (2 * o1 - ls) if row == rows - 1 else (2 * o1 + ls - 3)
+                if owner[g] == r:
+                    assert ids[ml, row] == g - firsts[r]
+                else:
+                    assert ids[ml, row] <= -2
+                    assert recv[r][-2 - ids[ml, row]] == (g, want_dir)
+        # cut interfaces still find the neighbour's face in their slot
+        ifg, L, R, dimi = p.array("if_global"), p.array("if_left"), p.array("if_right"), p.array("if_dim")
+        gl = c.interfaces.neighbor_ids
+        for s in range(ifg.shape[0]):
+            if L[s] <= -2:
+                assert recv[r][-2 - L[s]] == (gl[0, ifg[s]] - 1, 2 * dimi[s] + 1)
+            if R[s] <= -2:
+                assert recv[r][-2 - R[s]] == (gl[1, ifg[s]] - 1, 2 * dimi[s])
+    assert n_replicas.min() >= 1
+    CUT_SEEN[(name, nranks)] = int(n_replicas.max())
+
+
+CUT_SEEN = {}
+
+
+def test_some_partition_really_cuts_a_mortar():
+    """(runs after the parametrised test above) at least one of the rank counts replicates a mortar on 2+ ranks."""
+    if not CUT_SEEN:
+        pytest.skip("parametrised plan test did not run")
+    assert max(CUT_SEEN.values()) >= 2, CUT_SEEN
+
+
+def test_partition_rejects_bad_args():
     import trixib200 as T
-    mesh, basis, c, _ = _build(MESHES["box_3d"])
-    with pytest.raises(T.TrixiB200Error):
-        _plan(mesh, basis, 0, 2)
     mesh, basis, c, _ = _build(MESHES["uniform_3d"])
     with pytest.raises(T.TrixiB200Error):
         _plan(mesh, basis, 2, 2)

@@ -52,6 +52,7 @@ struct Dev {
   // halo
   const int* send_elem; const int* send_dir;  // [nhalo_send]
   double* halo_send; const double* halo_recv; // [nv, nf, nhalo]
+  double* halo_alpha_send; double* halo_alpha_recv;   // [nhalo]: indicator value of the element behind every exchanged face
   // physics
   EqPrm prm;
   int volume_integral, vol_flux, fv_flux, surf_flux, noncons, ic, src, ind_var, alpha_smooth;

@@ -175,18 +175,26 @@ __global__ void k_alpha_smooth_interfaces(Dev d) {
   int64_t s = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (s >= d.I) return;
   int l = d.if_left[s], r = d.if_right[s];
-  if (l < 0 || r < 0) return;  // halo-side smoothing handled by the alpha halo exchange
-  atomic_max_nonneg(&d.alpha[l], 0.5 * d.alpha_tmp[r]);
-  atomic_max_nonneg(&d.alpha[r], 0.5 * d.alpha_tmp[l]);
+  // a side on another rank: its indicator value arrived with the alpha halo exchange (slot = the face's halo slot);
+  // only the local side is updated, the owner of the other side does the mirror-image update
+  if (l >= 0) atomic_max_nonneg(&d.alpha[l], 0.5 * (r >= 0 ? d.alpha_tmp[r] : d.halo_alpha_recv[nb_halo_slot(r)]));
+  if (r >= 0) atomic_max_nonneg(&d.alpha[r], 0.5 * (l >= 0 ? d.alpha_tmp[l] : d.halo_alpha_recv[nb_halo_slot(l)]));
+}
+// indicator value of the element behind every face this rank sends (same order as the trace exchange)
+__global__ void k_pack_alpha(Dev d) {
+  int64_t s = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (s < d.nhalo_send) d.halo_alpha_send[s] = d.alpha_tmp[d.send_elem[s]];
 }
 __global__ void k_alpha_smooth_mortars(Dev d, int nsmall) {
   int64_t m = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (m >= d.M) return;
   int large = d.mo_ids[(nsmall + 1) * m + nsmall];
+  const double a_large = large >= 0 ? d.alpha_tmp[large] : d.halo_alpha_recv[nb_halo_slot(large)];
   for (int q = 0; q < nsmall; ++q) {
     int sm_ = d.mo_ids[(nsmall + 1) * m + q];
-    atomic_max_nonneg(&d.alpha[sm_], 0.5 * d.alpha_tmp[large]);
-    atomic_max_nonneg(&d.alpha[large], 0.5 * d.alpha_tmp[sm_]);
+    const double a_small = sm_ >= 0 ? d.alpha_tmp[sm_] : d.halo_alpha_recv[nb_halo_slot(sm_)];
+    if (sm_ >= 0) atomic_max_nonneg(&d.alpha[sm_], 0.5 * a_large);
+    if (large >= 0) atomic_max_nonneg(&d.alpha[large], 0.5 * a_small);
   }
 }
 
@@ -317,10 +325,15 @@ __global__ void k_prolong_mortars(Dev d, const double* __restrict__ u) {
   const Ops& op = *d.ops;
   int fixed_small = (ls == 1) ? 0 : N - 1, fixed_large = (ls == 1) ? N - 1 : 0;
   int a = f % N, b = (ND == 3) ? f / N : 0;
+  // face value of a participant: a local element's node, or (element on another rank) its received trace [f][v]
+  auto face_val = [&](int e, int fixed, int ff) -> double {
+    return e >= 0 ? u[(size_t)nv * nn * e + nv * face_node<ND>(N, dim, fixed, ff) + v]
+                  : d.halo_recv[(size_t)nv * (ff + (size_t)nf * nb_halo_slot(e)) + v];
+  };
   for (int q = 0; q < NS; ++q) {
     size_t o = 2 * (v + (size_t)nv * (f + (size_t)nf * m));
     int e = ids[mortar_small_row<ND>(q)];
-    d.mortar_u[q][o + (2 - ls)] = u[(size_t)nv * nn * e + nv * face_node<ND>(N, dim, fixed_small, f) + v];
+    d.mortar_u[q][o + (2 - ls)] = face_val(e, fixed_small, f);
     const double *M1, *M2;
     if (ND == 3) {
       M1 = (q == 0 || q == 2) ? op.fwd_l : op.fwd_u;
@@ -334,12 +347,12 @@ __global__ void k_prolong_mortars(Dev d, const double* __restrict__ u) {
       for (int bb = 0; bb < N; ++bb) {
         double t1 = 0;
         for (int aa = 0; aa < N; ++aa)
-          t1 += M1[a + N * aa] * u[(size_t)nv * nn * large + nv * face_node<ND>(N, dim, fixed_large, aa + N * bb) + v];
+          t1 += M1[a + N * aa] * face_val(large, fixed_large, aa + N * bb);
         s += M2[b + N * bb] * t1;
       }
     } else {
       for (int aa = 0; aa < N; ++aa)
-        s += M1[a + N * aa] * u[(size_t)nv * nn * large + nv * face_node<ND>(N, dim, fixed_large, aa) + v];
+        s += M1[a + N * aa] * face_val(large, fixed_large, aa);
     }
     d.mortar_u[q][o + (ls - 1)] = s;
   }
@@ -402,8 +415,9 @@ __global__ void k_mortar_to_elements(Dev d) {
   double total = 0;
   for (int q = 0; q < NS; ++q) {
     int e = ids[mortar_small_row<ND>(q)];
-    d.sfv[(size_t)nv * (f + (size_t)nf * (dir_small + (size_t)2 * ND * e)) + v] =
-        d.fstar_p[q][(size_t)nv * (f + (size_t)nf * m) + v];
+    if (e >= 0)      // (a replicated mortar: elements of other ranks take their fluxes from their own copy)
+      d.sfv[(size_t)nv * (f + (size_t)nf * (dir_small + (size_t)2 * ND * e)) + v] =
+          d.fstar_p[q][(size_t)nv * (f + (size_t)nf * m) + v];
     const double *M1, *M2;
     if (ND == 3) {
       M1 = (q == 0 || q == 2) ? op.rev_l : op.rev_u;
@@ -426,7 +440,7 @@ __global__ void k_mortar_to_elements(Dev d) {
     total += s;
   }
   int large = ids[NS];
-  d.sfv[(size_t)nv * (f + (size_t)nf * (dir_large + (size_t)2 * ND * large)) + v] = total;
+  if (large >= 0) d.sfv[(size_t)nv * (f + (size_t)nf * (dir_large + (size_t)2 * ND * large)) + v] = total;
 }
 
 // ------------------------------------------------------------------------------------------------

@@ -79,11 +79,14 @@ struct Plan {
   std::vector<int> send_elem, send_dir;                // peer-major send list (local element, 0-based direction)
   std::vector<int64_t> send_global_iface;              // global interface index of each send entry
   std::vector<int> peers;
-  std::vector<int64_t> peer_count;
+  std::vector<int64_t> peer_count;                     // faces RECEIVED from each peer (interface faces, then mortar faces)
+  std::vector<int64_t> peer_send_count;                // faces SENT to each peer (equal to peer_count without cut mortars)
+  int64_t nrecv = 0;
   std::vector<int> elems_interior, elems_halo;
   std::vector<int> bd_elem, bd_dim, bd_side, bd_dir;
   std::vector<int64_t> bd_global;
   std::vector<int> mo_ids, mo_side, mo_dim;
+  std::vector<int64_t> mo_global;                      // global mortar index of each local (possibly replicated) mortar
 };
 
 static int64_t range_first(int64_t EG, int nranks, int r) { return (int64_t)((__int128)EG * r / nranks); }
@@ -137,18 +140,72 @@ static int build_plan(const trixib200_config& c, const trixib200_mesh_host* ms, 
       }
     }
   }
-  // halo slots are peer-major; the k-th face exchanged with a peer has the same k on both sides because both
-  // ranks walk the global interface list in the same order
+  // ---- mortars whose elements live on several ranks are REPLICATED on every rank that owns one of them (SURVEY.md
+  // section 8(e)): the rank receives the face traces of the elements it does not own -- the same unit as a cut
+  // interface face -- and computes the whole mortar; it only keeps the fluxes of its own elements. Sender and
+  // receiver walk the global mortar list in the same order, so the k-th mortar face exchanged between two ranks has
+  // the same k on both sides; per peer the mortar faces come behind the interface faces.
+  const int rows = P.nsmall + 1;
+  struct MortarRecv { int64_t mortar_local; int row; int peer; int64_t k; };
+  std::vector<MortarRecv> mrecv;
+  std::vector<int64_t> recv_per_peer(per_peer);         // interface faces: one received per one sent
+  std::vector<char> touches_halo(E, 0);
+  for (int64_t m = 0; m < ms->nmortars; ++m) {
+    int own[5];
+    int64_t gid[5];
+    bool mine = false;
+    for (int r = 0; r < rows; ++r) {
+      gid[r] = ms->mortars_neighbor_ids[rows * m + r] - 1;
+      if (gid[r] < 0 || gid[r] >= EG) return fail(TRIXIB200_EINVAL, "bad mortar entry");
+      own[r] = (gid[r] >= first && gid[r] < last) ? c.rank : owner(gid[r]);
+      mine = mine || own[r] == c.rank;
+    }
+    if (!mine) continue;
+    const int o1 = (int)ms->mortars_orientations[m], ls = (int)ms->mortars_large_sides[m];
+    if (o1 < 1 || o1 > nd || (ls != 1 && ls != 2)) return fail(TRIXIB200_EINVAL, "bad mortar entry");
+    const int dir_small = 2 * o1 + ls - 3, dir_large = 2 * o1 - ls;      // 0-based face directions towards the mortar
+    std::vector<int> involved(own, own + rows);
+    std::sort(involved.begin(), involved.end());
+    involved.erase(std::unique(involved.begin(), involved.end()), involved.end());
+    const int64_t ml = (int64_t)P.mo_side.size();
+    for (int r = 0; r < rows; ++r) {
+      if (own[r] == c.rank) {
+        const int le = (int)(gid[r] - first);
+        P.mo_ids.push_back(le);
+        for (int b : involved)
+          if (b != c.rank) {
+            send_elem[b].push_back(le); send_dir[b].push_back(r == rows - 1 ? dir_large : dir_small);
+            send_gi[b].push_back(-1);
+            touches_halo[le] = 1;
+          }
+      } else {
+        P.mo_ids.push_back(0);                                           // halo code filled in below
+        mrecv.push_back({ml, r, own[r], recv_per_peer[own[r]]++});
+      }
+    }
+    P.mo_side.push_back(ls);
+    P.mo_dim.push_back(o1 - 1);
+    P.mo_global.push_back(m);
+  }
+  // halo slots are peer-major (receive order); the k-th interface face exchanged with a peer has the same k on both
+  // sides because both ranks walk the global interface list in the same order
   std::vector<int64_t> peer_off(c.nranks + 1, 0);
-  for (int p = 0; p < c.nranks; ++p) peer_off[p + 1] = peer_off[p] + per_peer[p];
+  for (int p = 0; p < c.nranks; ++p) peer_off[p + 1] = peer_off[p] + recv_per_peer[p];
+  P.nrecv = peer_off[c.nranks];
   for (int p = 0; p < c.nranks; ++p)
-    if (per_peer[p] > 0) { P.peers.push_back(p); P.peer_count.push_back(per_peer[p]); }
+    if (recv_per_peer[p] > 0 || !send_elem[p].empty()) {
+      P.peers.push_back(p); P.peer_count.push_back(recv_per_peer[p]); P.peer_send_count.push_back((int64_t)send_elem[p].size());
+    }
   for (int p = 0; p < c.nranks; ++p) {
     P.send_elem.insert(P.send_elem.end(), send_elem[p].begin(), send_elem[p].end());
     P.send_dir.insert(P.send_dir.end(), send_dir[p].begin(), send_dir[p].end());
     P.send_global_iface.insert(P.send_global_iface.end(), send_gi[p].begin(), send_gi[p].end());
   }
-  std::vector<char> touches_halo(E, 0);
+  for (const MortarRecv& mr : mrecv) {
+    int64_t slot = peer_off[mr.peer] + mr.k;
+    if (slot >= ((int64_t)1 << 30)) return fail(TRIXIB200_EUNSUPPORTED, "too many halo faces");
+    P.mo_ids[(size_t)rows * mr.mortar_local + mr.row] = nb_from_halo_slot((int)slot);
+  }
   for (const HaloRef& hr : halos) {
     int64_t slot = peer_off[hr.peer] + hr.k;
     if (slot >= ((int64_t)1 << 30)) return fail(TRIXIB200_EUNSUPPORTED, "too many halo faces");
@@ -178,17 +235,6 @@ static int build_plan(const trixib200_config& c, const trixib200_mesh_host* ms, 
     }
   }
   if (b != ms->nboundaries) return fail(TRIXIB200_EINVAL, "n_boundaries_per_direction does not sum to nboundaries");
-  // mortars
-  const int rows = P.nsmall + 1;
-  for (int64_t m = 0; m < ms->nmortars; ++m) {
-    for (int r = 0; r < rows; ++r) {
-      int64_t g = ms->mortars_neighbor_ids[rows * m + r] - 1;
-      if (g < first || g >= last) return fail(TRIXIB200_EUNSUPPORTED, "mortar crosses a partition boundary");
-      P.mo_ids.push_back((int)(g - first));
-    }
-    P.mo_side.push_back((int)ms->mortars_large_sides[m]);
-    P.mo_dim.push_back((int)ms->mortars_orientations[m] - 1);
-  }
   return 0;
 }
 
@@ -206,6 +252,7 @@ static bool plan_array(Plan* P, const std::string& n, const void** data, int64_t
   PA("if_left", if_left, 4) PA("if_right", if_right, 4) PA("if_dim", if_dim, 4) PA("if_global", if_global, 8)
   PA("face_nbr", face_nbr, 4) PA("send_elem", send_elem, 4) PA("send_dir", send_dir, 4)
   PA("send_global_iface", send_global_iface, 8) PA("peers", peers, 4) PA("peer_count", peer_count, 8)
+  PA("peer_send_count", peer_send_count, 8) PA("mo_side", mo_side, 4) PA("mo_dim", mo_dim, 4) PA("mo_global", mo_global, 8)
   PA("elems_interior", elems_interior, 4) PA("elems_halo", elems_halo, 4) PA("bd_elem", bd_elem, 4)
   PA("bd_global", bd_global, 8) PA("mo_ids", mo_ids, 4)
 #undef PA
@@ -247,7 +294,8 @@ struct trixib200_handle {
   int64_t n_interior = 0, n_halo_elems = 0;
   // halo plan
   std::vector<int> peers;                 // peer ranks
-  std::vector<int64_t> peer_count;        // faces exchanged with each peer (send == recv count)
+  std::vector<int64_t> peer_count;        // faces received from each peer
+  std::vector<int64_t> peer_send_count;   // faces sent to each peer (== peer_count unless mortars cross a cut)
   ncclComm_t comm = nullptr;
   int sm_count = 148;
   // in-kernel halo exchange over peer memory (CUDA IPC; see P2PArgs in kernels_line6.cuh)
@@ -414,9 +462,6 @@ static int create_impl(const trixib200_config* cfg, const trixib200_basis_host* 
     if (bc == TRIXIB200_BC_SLIP_WALL && c.equations != TRIXIB200_EQ_EULER)
       return fail(TRIXIB200_EUNSUPPORTED, "boundary_condition_slip_wall only for compressible Euler");
   }
-  if (c.nranks > 1 && ms->nmortars > 0) return fail(TRIXIB200_EUNSUPPORTED, "multi-GPU with mortars is not supported yet");
-  if (c.nranks > 1 && c.volume_integral == TRIXIB200_VI_SHOCK_CAPTURING_HG && c.alpha_smooth)
-    return fail(TRIXIB200_EUNSUPPORTED, "multi-GPU shock capturing with alpha_smooth is not supported yet");
 
   int ndev = 0;
   if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0)
@@ -471,7 +516,7 @@ static int create_impl(const trixib200_config* cfg, const trixib200_basis_host* 
   h->E_global = EG; h->first = first;
   d.E = E;
   if ((int64_t)d.nn * E * d.nv >= (int64_t)1 << 40) return fail(TRIXIB200_EUNSUPPORTED, "partition too large");
-  h->peers = P.peers; h->peer_count = P.peer_count;
+  h->peers = P.peers; h->peer_count = P.peer_count; h->peer_send_count = P.peer_send_count;
 
   // ---- elements
   {
@@ -495,7 +540,8 @@ static int create_impl(const trixib200_config* cfg, const trixib200_basis_host* 
   }
   // ---- interfaces + halo
   d.I = (int64_t)P.if_left.size();
-  d.nhalo_recv = d.nhalo_send = (int64_t)P.send_elem.size();
+  d.nhalo_send = (int64_t)P.send_elem.size();
+  d.nhalo_recv = P.nrecv;
   {
     int* p;
     if (int rc = upload(h, P.if_left, &p)) return rc; d.if_left = p;
@@ -506,6 +552,9 @@ static int create_impl(const trixib200_config* cfg, const trixib200_basis_host* 
     double* q;
     if (int rc = dalloc(h, (size_t)d.nv * d.nf * d.nhalo_send, &q)) return rc; d.halo_send = q;
     if (int rc = dalloc(h, (size_t)d.nv * d.nf * d.nhalo_recv, &q)) return rc; d.halo_recv = q;
+    // one value per exchanged face: the owner's indicator value, for smoothing across a cut
+    if (int rc = dalloc(h, (size_t)d.nhalo_send, &q)) return rc; d.halo_alpha_send = q;
+    if (int rc = dalloc(h, (size_t)d.nhalo_recv, &q)) return rc; d.halo_alpha_recv = q;
   }
   // ---- boundaries
   {
@@ -640,6 +689,21 @@ static int st_indicator(trixib200_handle* h, const double* u) {
   int threads = ((d.nn + 31) / 32) * 32;
   TB_DISPATCH_EQ(h, { if (d.E > 0) { k_indicator<Eq><<<(unsigned)d.E, threads, 2 * d.nn * sizeof(double), h->stream>>>(d, u); h->launches++; } });
   if (d.alpha_smooth) {
+    if (h->cfg.nranks > 1 && !h->peers.empty()) {
+      // indicator values of the elements behind the cut faces (one double per exchanged face), on the main stream
+      if (!h->comm) return fail(TRIXIB200_ECOMM, "nranks > 1 but trixib200_comm_init was not called");
+      LAUNCH(h, k_pack_alpha, d.nhalo_send, 128, 0, d);
+      int rc = g_nccl.GroupStart(), rc1 = 0;
+      size_t soff = 0, roff = 0;
+      for (size_t k = 0; k < h->peers.size() && rc == 0; ++k) {
+        const size_t sc = (size_t)h->peer_send_count[k], rcn = (size_t)h->peer_count[k];
+        if (sc > 0 && !rc1) rc1 = g_nccl.Send(d.halo_alpha_send + soff, sc, NCCL_FLOAT64, h->peers[k], h->comm, h->stream);
+        if (rcn > 0 && !rc1) rc1 = g_nccl.Recv(d.halo_alpha_recv + roff, rcn, NCCL_FLOAT64, h->peers[k], h->comm, h->stream);
+        soff += sc; roff += rcn;
+      }
+      if (rc == 0) rc = g_nccl.GroupEnd();
+      if (rc != 0 || rc1 != 0) return fail(TRIXIB200_ECOMM, "alpha halo exchange (ncclSend/ncclRecv) failed");
+    }
     LAUNCH(h, k_alpha_smooth_interfaces, d.I, 256, 0, d);
     LAUNCH(h, k_alpha_smooth_mortars, d.M, 128, 0, d, h->nsmall);
   }
@@ -647,7 +711,8 @@ static int st_indicator(trixib200_handle* h, const double* u) {
 }
 static int st_volume(trixib200_handle* h, double* du, const double* u) {
   Dev& d = h->d;
-  if (d.volume_integral == TRIXIB200_VI_SHOCK_CAPTURING_HG) st_indicator(h, u);
+  if (d.volume_integral == TRIXIB200_VI_SHOCK_CAPTURING_HG)
+    if (int rc = st_indicator(h, u)) return rc;
   TB_DISPATCH_EQ(h, LAUNCH(h, k_volume<Eq>, d.E * d.nn, 128, 0, d, du, u));
   return 0;
 }
@@ -704,7 +769,7 @@ static int st_epilogue(trixib200_handle* h, double* du, const double* u, double 
 // halo exchange: pack + NCCL send/recv on the comm stream, beside the interior elements on the main stream
 static int halo_begin(trixib200_handle* h, const double* u) {
   Dev& d = h->d;
-  if (h->cfg.nranks == 1 || d.nhalo_send == 0) return 0;
+  if (h->cfg.nranks == 1 || h->peers.empty()) return 0;
   if (!h->comm) return fail(TRIXIB200_ECOMM, "nranks > 1 but trixib200_comm_init was not called");
   // u is ready (and the previous rhs! is done with halo_recv) once the main stream reaches this point
   CUDA_TRY(cudaEventRecord(h->ev_pack, h->stream));
@@ -726,16 +791,20 @@ static int halo_begin(trixib200_handle* h, const double* u) {
   };
   int rc = g_nccl.GroupStart();
   if (rc != 0) return nccl_err("ncclGroupStart", rc);
-  size_t off = 0;
+  size_t soff = 0, roff = 0;
   int rc_first = 0;
   const char* what_first = nullptr;
   for (size_t k = 0; k < h->peers.size(); ++k) {
-    size_t cnt = per * (size_t)h->peer_count[k];
-    rc = g_nccl.Send(d.halo_send + off, cnt, NCCL_FLOAT64, h->peers[k], h->comm, h->comm_stream);
-    if (rc != 0 && !rc_first) { rc_first = rc; what_first = "ncclSend"; }
-    rc = g_nccl.Recv((void*)(d.halo_recv + off), cnt, NCCL_FLOAT64, h->peers[k], h->comm, h->comm_stream);
-    if (rc != 0 && !rc_first) { rc_first = rc; what_first = "ncclRecv"; }
-    off += cnt;
+    const size_t scnt = per * (size_t)h->peer_send_count[k], rcnt = per * (size_t)h->peer_count[k];
+    if (scnt > 0) {
+      rc = g_nccl.Send(d.halo_send + soff, scnt, NCCL_FLOAT64, h->peers[k], h->comm, h->comm_stream);
+      if (rc != 0 && !rc_first) { rc_first = rc; what_first = "ncclSend"; }
+    }
+    if (rcnt > 0) {
+      rc = g_nccl.Recv((void*)(d.halo_recv + roff), rcnt, NCCL_FLOAT64, h->peers[k], h->comm, h->comm_stream);
+      if (rc != 0 && !rc_first) { rc_first = rc; what_first = "ncclRecv"; }
+    }
+    soff += scnt; roff += rcnt;
   }
   rc = g_nccl.GroupEnd();       // always closed, also after a failed send / recv
   if (rc_first != 0) return nccl_err(what_first, rc_first);
@@ -744,14 +813,14 @@ static int halo_begin(trixib200_handle* h, const double* u) {
   return 0;
 }
 static int halo_wait(trixib200_handle* h) {
-  if (h->cfg.nranks == 1 || h->d.nhalo_send == 0) return 0;
+  if (h->cfg.nranks == 1 || h->peers.empty()) return 0;
   CUDA_TRY(cudaStreamWaitEvent(h->stream, h->ev_halo, 0));
   return 0;
 }
 
 static int rhs_staged(trixib200_handle* h, double* du, const double* u, double t) {
   if (int rc = halo_begin(h, u)) return rc;
-  st_volume(h, du, u);
+  if (int rc = st_volume(h, du, u)) return rc;
   if (int rc = halo_wait(h)) return rc;
   st_prolong_interfaces(h, u);
   st_interface_flux(h);
@@ -844,14 +913,20 @@ static int rhs_fused(trixib200_handle* h, double* du, const double* u, double t,
   }
   if (int rc = halo_begin(h, u)) return rc;
   if (tracing) { cudaEventRecord(g_trace.e[1], h->stream); cudaEventRecord(g_trace.e[5], h->comm_stream); }
-  if (d.volume_integral == TRIXIB200_VI_SHOCK_CAPTURING_HG) st_indicator(h, u);
+  if (d.volume_integral == TRIXIB200_VI_SHOCK_CAPTURING_HG)
+    if (int rc = st_indicator(h, u)) return rc;
   // faces the fused kernel does not compute itself: boundary and mortar faces -> surface_flux_values
   if (d.B > 0) { st_prolong_boundaries(h, u); st_boundary_flux(h, t); }
-  if (d.M > 0) { st_prolong_mortars(h, u); st_mortar_flux(h); }
-  bool multi = h->cfg.nranks > 1 && d.nhalo_send > 0;
+  bool multi = h->cfg.nranks > 1 && !h->peers.empty();
+  bool halo_here = false;
+  if (d.M > 0) {
+    // a mortar replicated on this rank may need face traces of elements on other ranks: they come with the halo
+    if (multi) { if (int rc = halo_wait(h)) return rc; halo_here = true; }
+    st_prolong_mortars(h, u); st_mortar_flux(h);
+  }
   // (the line-owner / warp-per-element kernels need 16-byte aligned vectors; fused_launch_any checks)
   auto launch = [&](const int* elems, int64_t count) -> int { return fused_launch_any(h, du, u, t, elems, count, rk); };
-  if (!multi) {
+  if (!multi || halo_here) {
     if (int rc = launch(nullptr, d.E)) return rc;
   } else {
     // (TRIXIB200_TRACE on 2 GPUs, level 7: pack 0.03-0.04 ms, exchange complete 0.12 ms after the start -- it runs
@@ -1020,7 +1095,7 @@ extern "C" int trixib200_stage(trixib200_handle* h, const char* stage, double* d
   std::string n(stage);
   Dev& d = h->d;
   if (n == "reset_du") CUDA_TRY(cudaMemsetAsync(du, 0, sizeof(double) * d.E * d.nn * d.nv, h->stream));
-  else if (n == "calc_volume_integral") st_volume(h, du, u);
+  else if (n == "calc_volume_integral") { if (int rc = st_volume(h, du, u)) return rc; }
   else if (n == "prolong2interfaces") {
     if (int rc = halo_begin(h, u)) return rc;
     if (int rc = halo_wait(h)) return rc;
@@ -1034,7 +1109,7 @@ extern "C" int trixib200_stage(trixib200_handle* h, const char* stage, double* d
   else if (n == "calc_surface_integral") st_epilogue(h, du, u, t, 1);
   else if (n == "apply_jacobian") st_epilogue(h, du, u, t, 2);
   else if (n == "calc_sources") st_epilogue(h, du, u, t, 4);
-  else if (n == "calc_indicator") st_indicator(h, u);
+  else if (n == "calc_indicator") { if (int rc = st_indicator(h, u)) return rc; }
   else return fail(TRIXIB200_EINVAL, "unknown stage " + n);
   CUDA_TRY(cudaGetLastError());
   CUDA_TRY(cudaStreamSynchronize(h->stream));
@@ -1423,7 +1498,7 @@ static int p2p_setup(trixib200_handle* h) {
     return 0;
   }
   std::vector<int> first(np + 1, 0), ranks(np, 0);
-  for (size_t k = 0; k < np; ++k) { first[k + 1] = first[k] + (int)h->peer_count[k]; ranks[k] = h->peers[k]; }
+  for (size_t k = 0; k < np; ++k) { first[k + 1] = first[k] + (int)h->peer_send_count[k]; ranks[k] = h->peers[k]; }
   if (int rc = upload(h, first, &P.d_peer_first)) return rc;
   if (int rc = upload(h, ranks, &P.d_peer_rank)) return rc;
   if (int rc = upload(h, dst[0], &P.d_peer_dst[0])) return rc;
