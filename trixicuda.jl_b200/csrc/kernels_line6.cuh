@@ -180,6 +180,7 @@ constexpr int l6_maxnreg(int warps, int ctas) {
 #endif
 template <int REGS> TB_D void l6_reg_inc() { asm volatile("setmaxnreg.inc.sync.aligned.u32 %0;\n" ::"n"(REGS)); }
 template <int REGS> TB_D void l6_reg_dec() { asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;\n" ::"n"(REGS)); }
+TB_D int l6_pp_bar(int wg, int round) { return 1 + 2 * wg + (round & 1); }    // ids 1..6
 TB_D void l6_bar_sync(int id, int n) { asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(n) : "memory"); }
 TB_D void l6_bar_arrive(int id, int n) { asm volatile("bar.arrive %0, %1;" ::"r"(id), "r"(n) : "memory"); }
 // the same, issued once `dep` has been computed (ptxas moves arithmetic across a volatile asm, a data dependence pins it)
@@ -345,10 +346,12 @@ k_line6(const __grid_constant__ Dev d, const __grid_constant__ LineOps ops, doub
   const int niter = PP ? (npairs + nw - 1) / nw : 0;
   if (PP) {
     l6_reg_dec<L6_PP_LO>();
-    // barrier 1 + k lets warpgroup k into its flux part; it is raised by warpgroup (k + 3 - TOKENS) % 3 when that one
-    // leaves a flux part, and once at the start for the first TOKENS warpgroups
+    // barrier l6_pp_bar(k, n) lets warpgroup k into its n-th flux part; it is raised by warpgroup (k + 3 - TOKENS) % 3
+    // when that one leaves a flux part, and once at the start for the first TOKENS warpgroups. With two tokens a
+    // warpgroup can be handed its next TWO entries before it takes the first (never three), so consecutive entries
+    // use different barriers (parity of n): a named barrier must not collect two rounds of arrivals.
     for (int k = 0; k < L6_PP_TOKENS; ++k)
-      if (wg == (k + 3 - L6_PP_TOKENS) % 3) l6_bar_arrive(1 + k, 256);
+      if (wg == (k + 3 - L6_PP_TOKENS) % 3) l6_bar_arrive(l6_pp_bar(k, 0), 256);
   }
   unsigned fbits = 0;
   int pr = wid;
@@ -516,7 +519,7 @@ k_line6(const __grid_constant__ Dev d, const __grid_constant__ LineOps ops, doub
         // the running sums too (40 more registers live across the wait)
         load_old(0, acc[0]); load_old(1, acc[1]); load_old(2, acc[2]); load_old(3, acc[3]);
 #endif
-        l6_bar_sync(1 + wg, 256);      // token: this warpgroup's turn on the FP64 pipe
+        l6_bar_sync(l6_pp_bar(wg, 3 * it + step), 256);      // token: this warpgroup's turn on the FP64 pipe
         l6_reg_inc<L6_PP_HI>();
 #ifndef L6_PP_ACC_EARLY
         load_old(0, acc[0]); load_old(1, acc[1]); load_old(2, acc[2]); load_old(3, acc[3]);
@@ -569,7 +572,8 @@ k_line6(const __grid_constant__ Dev d, const __grid_constant__ LineOps ops, doub
           // PP: the next warpgroup is woken a little before this one gives its registers back, so that its wake-up
           // latency is hidden behind the last accumulations
           if (PP && L6_PP_TOKENS == 1 && K0 + k == L6_PP_ARRIVE_K)
-            l6_bar_arrive_after(1 + (wg + L6_PP_TOKENS) % 3, 256, acc[L6_PB[K0 + k] - 1 > 3 ? 3 : L6_PB[K0 + k] - 1][NV - 1]);
+            l6_bar_arrive_after(l6_pp_bar((wg + L6_PP_TOKENS) % 3, (3 * (3 * it + step) + wg + L6_PP_TOKENS) / 3), 256,
+                                acc[L6_PB[K0 + k] - 1 > 3 ? 3 : L6_PB[K0 + k] - 1][NV - 1]);
         }
         if (FAST && worst >= L6_ROUGH_HI) {
 #pragma unroll
@@ -596,11 +600,12 @@ k_line6(const __grid_constant__ Dev d, const __grid_constant__ LineOps ops, doub
           // the 8 fluxes are accumulated: registers and token go to the next warpgroup (warpgroup 0
           // absorbs the last one behind the loop)
 #if L6_PP_TOKENS == 1
-          if (L6_PP_ARRIVE_K >= 8) l6_bar_arrive(1 + (wg + L6_PP_TOKENS) % 3, 256);
+          if (L6_PP_ARRIVE_K >= 8)
+            l6_bar_arrive(l6_pp_bar((wg + L6_PP_TOKENS) % 3, (3 * (3 * it + step) + wg + L6_PP_TOKENS) / 3), 256);
           l6_reg_dec<L6_PP_LO>();
 #else
           l6_reg_dec<L6_PP_LO>();        // with two tokens the registers must be back before the next one is let in
-          l6_bar_arrive(1 + (wg + L6_PP_TOKENS) % 3, 256);
+          l6_bar_arrive(l6_pp_bar((wg + L6_PP_TOKENS) % 3, (3 * (3 * it + step) + wg + L6_PP_TOKENS) / 3), 256);
 #endif
           relane();
           repos();
@@ -705,7 +710,7 @@ k_line6(const __grid_constant__ Dev d, const __grid_constant__ LineOps ops, doub
     e = e_next; valid = valid_next; fbits = fbits_next;
   }
   cp_async_wait<0>();
-  if (PP && wg < L6_PP_TOKENS) l6_bar_sync(1 + wg, 256);   // takes the token that was passed on after the CTA's last flux parts
+  if (PP && wg < L6_PP_TOKENS) l6_bar_sync(l6_pp_bar(wg, 3 * niter), 256);   // the token passed on after the CTA's last flux parts
 }
 
 // ---------------------------------------------------------------------------------------------- host side

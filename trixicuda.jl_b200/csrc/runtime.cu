@@ -323,11 +323,13 @@ struct trixib200_handle {
   struct HostPipe {
     bool built = false, usable = false;
     int64_t ce = 0, nchunks = 0;
-    std::vector<int> upload_order;         // chunk ids in upload order
-    std::vector<std::vector<int>> ready;   // ready[i]: chunks computable once upload_order[i] has landed
+    struct Run { int64_t first, count; };   // contiguous elements of the Morton order
+    std::vector<std::vector<Run>> runs;    // per slab
+    std::vector<int64_t> slab_off;         // [nslabs + 1] offsets into d_iota (elements grouped by slab)
+    std::vector<std::vector<int>> ready;   // ready[i]: slabs computable once slab i has landed
     std::vector<cudaEvent_t> ev_in, ev_done;
     cudaStream_t s_in = nullptr, s_out = nullptr;
-    int* d_iota = nullptr;
+    int* d_iota = nullptr;                 // element ids grouped by slab
   } pipe;
 };
 
@@ -964,11 +966,14 @@ extern "C" int trixib200_rhs(trixib200_handle* h, double* du, const double* u, d
 }
 
 // ---------------------------------------------------------------------------------------------- rhs on host vectors
-// Chunk pipeline of trixib200_rhs_host. The local elements are cut into contiguous chunks of the Morton order; chunks
-// are uploaded in the order of their last-dimension coordinate (thin layers), a chunk's elements are computed as soon
-// as the chunks holding all their face neighbours have landed, and its du is downloaded right after: upload, kernels
-// and download overlap (PCIe is full duplex) instead of running back to back. Used when one fused launch is the whole
-// rhs! (single rank, no boundary / mortar faces, no shock-capturing indicator pass); otherwise the plain sequence.
+// Slab pipeline of trixib200_rhs_host. The local elements are grouped into slabs by their last-dimension coordinate
+// (TRIXIB200_HOST_SLABS of them, default 16: thin layers of the mesh). Slabs are uploaded in order -- one copy per
+// contiguous run of the Morton order inside the slab --, a slab is computed with ONE launch over its element list as
+// soon as the slabs holding all its face neighbours have landed, and its du goes back right after: upload, kernels and
+// download overlap (PCIe is full duplex) instead of running back to back. Thinner slabs shorten the fill and drain of
+// the pipeline (tools/host_pipe_model.py); round 1 launched one kernel per 4096-element chunk, which made thin slabs
+// cost more in launches than they saved. Used when one fused launch is the whole rhs! (single rank, no boundary /
+// mortar faces, no shock-capturing indicator pass); otherwise the plain sequence.
 static int build_host_pipe(trixib200_handle* h) {
   auto& P = h->pipe;
   P.built = true;
@@ -976,44 +981,65 @@ static int build_host_pipe(trixib200_handle* h) {
   P.usable = h->fused && h->cfg.nranks == 1 && d.B == 0 && d.M == 0 &&
              d.volume_integral != TRIXIB200_VI_SHOCK_CAPTURING_HG && !h->face_nbr_host.empty();
   const int64_t E = d.E;
-  int64_t ce = 4096;   // elements per chunk (10 MB of 3D Euler state); TRIXIB200_HOST_CHUNK overrides (tests, tuning)
+  int64_t ce = 4096;   // the pipeline pays from ~4 such chunks on; TRIXIB200_HOST_CHUNK lowers the threshold (tests)
   const char* env = getenv("TRIXIB200_HOST_CHUNK");
   if (env && atoll(env) >= 64) ce = atoll(env);
   P.usable = P.usable && E >= 4 * ce;
   if (!P.usable) return 0;
   P.ce = ce;
-  P.nchunks = (E + ce - 1) / ce;
+  int want = 16;
+  const char* es = getenv("TRIXIB200_HOST_SLABS");
+  if (es && atoi(es) >= 2) want = atoi(es);
+  // distinct layers of the last coordinate -> slab of every element
+  std::vector<double> keys(h->chunk_key_src);
+  std::sort(keys.begin(), keys.end());
+  keys.erase(std::unique(keys.begin(), keys.end()), keys.end());
+  const int64_t nlayers = (int64_t)keys.size();
+  const int64_t S = std::max<int64_t>(2, std::min<int64_t>(want, nlayers));
+  P.nchunks = S;
+  std::vector<int> slab((size_t)E);
+  for (int64_t e = 0; e < E; ++e) {
+    const int64_t layer = std::lower_bound(keys.begin(), keys.end(), h->chunk_key_src[e]) - keys.begin();
+    slab[e] = (int)(layer * S / nlayers);
+  }
+  // element list per slab (ascending element id), contiguous runs inside it
+  std::vector<int64_t> cnt(S + 1, 0);
+  for (int64_t e = 0; e < E; ++e) cnt[slab[e] + 1]++;
+  for (int64_t q = 0; q < S; ++q) cnt[q + 1] += cnt[q];
+  P.slab_off.assign(cnt.begin(), cnt.end());
+  std::vector<int> elems((size_t)E);
+  {
+    std::vector<int64_t> pos(cnt.begin(), cnt.end() - 1);
+    for (int64_t e = 0; e < E; ++e) elems[pos[slab[e]]++] = (int)e;
+  }
+  P.runs.assign(S, {});
+  for (int64_t q = 0; q < S; ++q)
+    for (int64_t k = P.slab_off[q]; k < P.slab_off[q + 1];) {
+      int64_t k1 = k + 1;
+      while (k1 < P.slab_off[q + 1] && elems[k1] == elems[k1 - 1] + 1) ++k1;
+      P.runs[q].push_back({(int64_t)elems[k], k1 - k});
+      k = k1;
+    }
+  // a slab can be computed once every slab that holds a face neighbour of one of its elements has landed
   const int nf = 2 * d.ndim;
-  // upload order: by the last-dimension coordinate of the chunk's first element, ties in Morton order
-  std::vector<int> order(P.nchunks);
-  for (int64_t c = 0; c < P.nchunks; ++c) order[c] = (int)c;
-  std::stable_sort(order.begin(), order.end(), [&](int a, int b) {
-    return h->chunk_key_src[(size_t)a * ce] < h->chunk_key_src[(size_t)b * ce];
-  });
-  std::vector<int> upos(P.nchunks);
-  for (int64_t i = 0; i < P.nchunks; ++i) upos[order[i]] = (int)i;
-  P.upload_order = order;
-  P.ready.assign(P.nchunks, {});
-  for (int64_t c = 0; c < P.nchunks; ++c) {
-    int r = upos[c];
-    const int64_t e0 = c * ce, e1 = std::min(E, e0 + ce);
-    for (int64_t e = e0; e < e1; ++e)
+  P.ready.assign(S, {});
+  for (int64_t q = 0; q < S; ++q) {
+    int r = (int)q;
+    for (int64_t k = P.slab_off[q]; k < P.slab_off[q + 1]; ++k)
       for (int f = 0; f < nf; ++f) {
-        const int code = h->face_nbr_host[(size_t)e * nf + f];
-        if (code >= 0) r = std::max(r, upos[code / ce]);
+        const int code = h->face_nbr_host[(size_t)elems[k] * nf + f];
+        if (code >= 0) r = std::max(r, slab[code]);
       }
-    P.ready[r].push_back((int)c);
+    P.ready[r].push_back((int)q);
   }
   CUDA_TRY(cudaStreamCreateWithFlags(&P.s_in, cudaStreamNonBlocking));
   CUDA_TRY(cudaStreamCreateWithFlags(&P.s_out, cudaStreamNonBlocking));
-  P.ev_in.resize(P.nchunks); P.ev_done.resize(P.nchunks);
-  for (int64_t c = 0; c < P.nchunks; ++c) {
+  P.ev_in.resize(S); P.ev_done.resize(S);
+  for (int64_t c = 0; c < S; ++c) {
     CUDA_TRY(cudaEventCreateWithFlags(&P.ev_in[c], cudaEventDisableTiming));
     CUDA_TRY(cudaEventCreateWithFlags(&P.ev_done[c], cudaEventDisableTiming));
   }
-  std::vector<int> iota((size_t)E);
-  for (int64_t e = 0; e < E; ++e) iota[e] = (int)e;
-  if (int rc = upload(h, iota, &P.d_iota)) return rc;
+  if (int rc = upload(h, elems, &P.d_iota)) return rc;
   return 0;
 }
 
@@ -1053,21 +1079,21 @@ extern "C" int trixib200_rhs_host(trixib200_handle* h, double* du_host, const do
     cudaGetLastError();
   }
   for (int64_t i = 0; i < P.nchunks; ++i) {
-    const int cu = P.upload_order[i];
-    const int64_t e0 = (int64_t)cu * P.ce, cnt = std::min<int64_t>(d.E - e0, P.ce);
-    CUDA_TRY(cudaMemcpyAsync(h->host_u + per * e0, u_host + per * e0, per * cnt * sizeof(double),
-                             cudaMemcpyHostToDevice, P.s_in));
+    for (const auto& run : P.runs[i])
+      CUDA_TRY(cudaMemcpyAsync(h->host_u + per * run.first, u_host + per * run.first, per * run.count * sizeof(double),
+                               cudaMemcpyHostToDevice, P.s_in));
     CUDA_TRY(cudaEventRecord(P.ev_in[i], P.s_in));
     if (P.ready[i].empty()) continue;
     CUDA_TRY(cudaStreamWaitEvent(h->stream, P.ev_in[i], 0));
     for (int c : P.ready[i]) {
-      const int64_t c0 = (int64_t)c * P.ce, ccnt = std::min<int64_t>(d.E - c0, P.ce);
-      if (int rc = fused_launch_any(h, du_direct ? du_direct : h->host_du, h->host_u, t, P.d_iota + c0, ccnt)) return rc;
+      if (int rc = fused_launch_any(h, du_direct ? du_direct : h->host_du, h->host_u, t, P.d_iota + P.slab_off[c],
+                                    P.slab_off[c + 1] - P.slab_off[c])) return rc;
       if (du_direct) continue;
       CUDA_TRY(cudaEventRecord(P.ev_done[c], h->stream));
       CUDA_TRY(cudaStreamWaitEvent(P.s_out, P.ev_done[c], 0));
-      CUDA_TRY(cudaMemcpyAsync(du_host + per * c0, h->host_du + per * c0, per * ccnt * sizeof(double),
-                               cudaMemcpyDeviceToHost, P.s_out));
+      for (const auto& run : P.runs[c])
+        CUDA_TRY(cudaMemcpyAsync(du_host + per * run.first, h->host_du + per * run.first,
+                                 per * run.count * sizeof(double), cudaMemcpyDeviceToHost, P.s_out));
     }
   }
   CUDA_TRY(cudaStreamSynchronize(P.s_out));
