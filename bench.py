@@ -500,6 +500,8 @@ def run_ours(args):
                "api": "SemidiscretizationHyperbolicGPU.rhs_host -> trixib200_rhs_host (pinned host u, du)"}
         del u_host, du_host
     clocks.stop()
+    if world > 1:
+        _KEEP.extend([semi, u, du])
 
     if rank != 0:
         return 0
@@ -569,18 +571,32 @@ def semi_kernel_name(semi):
     return "k_warp3d" if semi.warp3d else "k_fused"
 
 
+_KEEP = []     # multi-rank runs: objects whose destructors must not run before the process leaves (see main)
+
+
 def main():
     args = parse()
     if args.impl == "reference":
         rc = run_reference(args)
     else:
         rc = run_ours(args)
+    multi = False
     try:
         import torch.distributed as dist
-        if dist.is_initialized():
+        multi = dist.is_initialized() and dist.get_world_size() > 1
+        if multi:
+            dist.barrier()      # every rank has finished its timed work and rank 0 has printed the line
+        elif dist.is_initialized():
             dist.destroy_process_group()
     except Exception:
         pass
+    sys.stdout.flush()
+    sys.stderr.flush()
+    if multi:
+        # Leave without running destructors: communicator / IPC teardown is not part of the benchmark, and an 8-rank
+        # run that had already printed its line once hung in teardown until it was killed (profiles/r2_bench_n8.json
+        # came from that run). The driver of the GPUs releases everything when the process ends.
+        os._exit(rc)
     return rc
 
 

@@ -40,6 +40,7 @@ struct Nccl {
   int (*GetUniqueId)(ncclUniqueId*) = nullptr;
   int (*CommInitRank)(ncclComm_t*, int, ncclUniqueId, int) = nullptr;
   int (*CommDestroy)(ncclComm_t) = nullptr;
+  int (*CommAbort)(ncclComm_t) = nullptr;
   int (*Send)(const void*, size_t, int, int, ncclComm_t, cudaStream_t) = nullptr;
   int (*Recv)(void*, size_t, int, int, ncclComm_t, cudaStream_t) = nullptr;
   int (*AllReduce)(const void*, void*, size_t, int, int, ncclComm_t, cudaStream_t) = nullptr;
@@ -55,7 +56,7 @@ struct Nccl {
     if (!lib) lib = dlopen("libnccl.so", RTLD_NOW);
     if (!lib) return false;
 #define SYM(n) *(void**)(&n) = dlsym(lib, "nccl" #n)
-    SYM(GetUniqueId); SYM(CommInitRank); SYM(CommDestroy); SYM(Send); SYM(Recv); SYM(AllReduce); SYM(AllGather);
+    SYM(GetUniqueId); SYM(CommInitRank); SYM(CommDestroy); SYM(CommAbort); SYM(Send); SYM(Recv); SYM(AllReduce); SYM(AllGather);
     SYM(GroupStart); SYM(GroupEnd); SYM(GetErrorString);
 #undef SYM
     return GetUniqueId && CommInitRank && Send && Recv && AllReduce && GroupStart && GroupEnd;
@@ -409,9 +410,19 @@ extern "C" int trixib200_destroy(trixib200_handle* h) {
   if (!h) return 0;
   cudaSetDevice(h->cfg.device);
   if (h->stream) cudaStreamSynchronize(h->stream);
-  for (void* pb : h->p2p.peer_base) if (pb) cudaIpcCloseMemHandle(pb);
-  if (h->p2p.base) cudaFree(h->p2p.base);
-  if (h->comm && g_nccl.CommDestroy) g_nccl.CommDestroy(h->comm);
+  // Teardown must not depend on what the other ranks are doing: handles are destroyed by garbage collectors and at
+  // interpreter exit, in no agreed order (an 8-rank run that printed its result hung in here until it was killed,
+  // profiles/r2_pytest_multi_8.log). Hence: the stream is idle (synchronised above), so the communicator is released
+  // with ncclCommAbort (local, never waits for a peer; ncclCommDestroy finalises collectively), the peers' buffers are
+  // unmapped, and this rank's exported receive buffer is NOT freed while peers may still have it mapped (freeing
+  // exported memory before every importer has closed it is undefined): it goes back with the context.
+  bool had_peers = false;
+  for (void* pb : h->p2p.peer_base) if (pb) { cudaIpcCloseMemHandle(pb); had_peers = true; }
+  if (h->p2p.base && !had_peers) cudaFree(h->p2p.base);
+  if (h->comm) {
+    if (h->cfg.nranks > 1 && g_nccl.CommAbort) g_nccl.CommAbort(h->comm);
+    else if (g_nccl.CommDestroy) g_nccl.CommDestroy(h->comm);
+  }
   for (void* p : h->allocs) cudaFree(p);
   if (h->ev_pack) cudaEventDestroy(h->ev_pack);
   if (h->ev_halo) cudaEventDestroy(h->ev_halo);
