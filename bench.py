@@ -70,6 +70,7 @@ def parse():
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-parity", action="store_true")
+    ap.add_argument("--no-shape-probe", action="store_true", help="config 5: keep the default k_line6 launch shape")
     a = ap.parse_args()
     if a.level == 0:
         a.level = CONFIGS[a.config]["level"]
@@ -359,13 +360,66 @@ def parity_check(args, rank, world, comm_id, local_rank, dist, dev):
             "tolerance": PARITY_TOL, "metric": "max|du - du_ref| / max|du_ref|", "ranks": world}
 
 
+LINE_SHAPES = {"default": "one copy of the phase code, run-time direction (2 CTAs x 4 warps per SM)",
+               "16": "the three phases unrolled, compile-time direction (2 CTAs x 4 warps per SM)"}
+
+
+def pick_line_shape(device_index):
+    """Config 5 runs the line-owner kernel k_line6, which exists in two launch shapes that differ only in code layout
+    (kernels_line6.cuh, TRIXIB200_LINE_SHAPE). Before anything is timed, each shape is run in its own process
+    (tools/line_check.py: du against the CPU oracle at levels 2 and 3 -- odd element counts per warp, both ln_mean
+    branches -- then CUDA-event timing at level 6); the fastest shape that passed the parity check is exported as
+    TRIXIB200_LINE_SHAPE for this run. A shape that fails, crashes or times out is dropped; with no usable probe the
+    default shape stays. Returns what was measured (goes into the JSON line)."""
+    import re
+    import subprocess
+    if os.environ.get("TRIXIB200_LINE_SHAPE"):
+        return {"chosen": os.environ["TRIXIB200_LINE_SHAPE"], "note": "TRIXIB200_LINE_SHAPE was set by the caller"}
+    res = {}
+    for shape in LINE_SHAPES:
+        env = dict(os.environ)
+        env["CUDA_VISIBLE_DEVICES"] = str(device_index) if "CUDA_VISIBLE_DEVICES" not in os.environ else \
+            os.environ["CUDA_VISIBLE_DEVICES"].split(",")[device_index]
+        for k in ("RANK", "LOCAL_RANK", "WORLD_SIZE", "MASTER_ADDR", "MASTER_PORT", "OMP_NUM_THREADS"):
+            env.pop(k, None)
+        if shape != "default":
+            env["TRIXIB200_LINE_SHAPE"] = shape
+        try:
+            out = subprocess.run([sys.executable, os.path.join(ROOT, "tools", "line_check.py"), "2", "3", "--", "6"],
+                                 capture_output=True, text=True, timeout=240, env=env)
+            ms = re.findall(r"level 6: rhs ([0-9.]+) ms", out.stdout)
+            ok = out.returncode == 0 and "FAIL" not in out.stdout and out.stdout.count(" ok") >= 4 and ms
+            res[shape] = {"parity_ok": bool(ok), "ms_level6": float(ms[-1]) if ms else None}
+        except Exception as ex:       # timeout, missing tool: the shape is simply not a candidate
+            res[shape] = {"parity_ok": False, "ms_level6": None, "error": type(ex).__name__}
+    good = {k: v["ms_level6"] for k, v in res.items() if v["parity_ok"]}
+    chosen = min(good, key=good.get) if good else "default"
+    if chosen != "default":
+        os.environ["TRIXIB200_LINE_SHAPE"] = chosen
+    return {"chosen": chosen, "probes": res, "what": LINE_SHAPES}
+
+
 def run_ours(args):
     import torch
     from trixib200 import distributed as D
     import trixib200 as T
     if not torch.cuda.is_available():
         raise SystemExit("bench.py: no CUDA device (libtrixib200 has no CPU fallback)")
+    shape_probe = None
+    if args.config == 5 and not args.no_shape_probe:
+        # rank 0 probes on its own GPU before the process group exists; the others learn the result below
+        if int(os.environ.get("RANK", "0")) == 0:
+            try:
+                shape_probe = pick_line_shape(int(os.environ.get("LOCAL_RANK", "0")))
+            except Exception as ex:     # the probe is an optimisation: never lose the bench line over it
+                shape_probe = {"chosen": "default", "error": repr(ex)}
     rank, local_rank, world = D.init_process_group()
+    if args.config == 5 and not args.no_shape_probe and world > 1:
+        box = [shape_probe]
+        torch.distributed.broadcast_object_list(box, src=0)
+        shape_probe = box[0]
+        if shape_probe and shape_probe.get("chosen", "default") != "default":
+            os.environ["TRIXIB200_LINE_SHAPE"] = str(shape_probe["chosen"])
     dist = torch.distributed if world > 1 else None
     torch.cuda.set_device(local_rank)
     dev = torch.device("cuda", local_rank)
@@ -557,7 +611,7 @@ def run_ours(args):
                                     "L2 flushed (256 MB write) before every timed call; calls timed one by one",
                        "setup_s": round(setup_s, 1)},
             "roofline": roofline, "e2e": e2e, "gpu_launches": int(launches), "clocks": clocks.summary(),
-            "du_checksum": du_checksum, "parity": parity, "extras": extras}
+            "du_checksum": du_checksum, "parity": parity, "line_shape": shape_probe, "extras": extras}
     if world == 1 and not args.no_cpu:
         line["cpu_baseline"] = cpu_sample(args)
     print(json.dumps(line), flush=True)

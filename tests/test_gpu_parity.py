@@ -486,3 +486,17 @@ def test_rhs_matches_oracle_at_baseline_sizes(name, level):
     if c["vi"] == "shock_capturing_hg":
         assert np.abs(semi.cache("alpha") - o.f64("alpha")).max() <= 1e-12
     assert abs(semi.max_dt(u_d, 0.0) / o.max_dt(u) - 1) <= 1e-13
+
+
+@pytest.mark.parametrize("shape", ["12", "16"])
+def test_line_kernel_launch_shapes_match_oracle(shape):
+    """The alternative launch shapes of k_line6 (TRIXIB200_LINE_SHAPE, read once per process -> own process): the
+    ping-pong shape and the unrolled phases that bench.py may select. du against the oracle at
+    levels 2 and 3 (weak blast wave and a rough state that takes both ln_mean branches), 1e-12."""
+    import subprocess, sys
+    root = _os.path.dirname(_os.path.dirname(_os.path.abspath(__file__)))
+    env = dict(_os.environ, TRIXIB200_LINE_SHAPE=shape)
+    res = subprocess.run([sys.executable, _os.path.join(root, "tools", "line_check.py"), "2", "3"],
+                         capture_output=True, text=True, timeout=600, env=env)
+    assert res.returncode == 0 and "FAIL" not in res.stdout, res.stdout[-2000:] + res.stderr[-2000:]
+    assert res.stdout.count(" ok") == 4, res.stdout[-2000:]

@@ -195,8 +195,11 @@ TB_D void l6_bar_arrive_after(int id, int n, double dep) {
 // half) starts that many cycles late, so that the two warps of a scheduler are not in the same part of an iteration.
 __device__ int l6_stagger_cycles = 0;
 
+// UNR: the three phases as three copies of the code (direction, slot rotation and the first / last phase special
+// cases are compile-time) instead of one copy with run-time selection: fewer executed instructions, 2.2x the hot
+// loop's code size (TRIXIB200_LINE_SHAPE=16; bench.py times both and keeps the faster one).
 template <int VFLUX, int SFLUX, bool SFV, int WARPS, int CTAS, int NP, bool RK = false, bool TOUT = false,
-          bool PP = false>
+          bool PP = false, bool UNR = false>
 __global__ void __launch_bounds__(32 * WARPS) __maxnreg__(l6_maxnreg(WARPS, CTAS))
 k_line6(const __grid_constant__ Dev d, const __grid_constant__ LineOps ops, double* __restrict__ du,
         const double* __restrict__ u, double t, const int* __restrict__ elems, int64_t count,
@@ -416,11 +419,7 @@ k_line6(const __grid_constant__ Dev d, const __grid_constant__ LineOps ops, doub
     }
     __syncwarp();
 
-#ifdef L6_UNROLL_PHASES
-#pragma unroll
-#else
-#pragma unroll 1
-#endif
+#pragma unroll(UNR ? 3 : 1)
     for (int step = 0; step < 3; ++step) {
       const int dir = 2 - step;
       if (PP) relane();
@@ -735,11 +734,11 @@ k_line6(const __grid_constant__ Dev d, const __grid_constant__ LineOps ops, doub
 // kernel's time follows the SUM of the issue costs of its instructions, not the occupancy: 1 warp per scheduler already
 // reaches 70 % of the throughput of 2, and 3 add nothing (profiles/r1_line6_notes.md).
 template <int VFLUX, int SFLUX, bool SFV, int CTAS, int WARPS, int NP, bool RK = false, bool TOUT = false,
-          bool PP = false>
+          bool PP = false, bool UNR = false>
 static int line6_launch_t(const Dev& d, const LineOps& ops, double* du, const double* u, double t, const int* elems,
                           int64_t count, cudaStream_t stream, int sm_count, const RkArgs& rk = RkArgs{nullptr, 0, 0, 0},
                           const P2PArgs& p2p = P2PArgs{}) {
-  auto kern = k_line6<VFLUX, SFLUX, SFV, WARPS, CTAS, NP, RK, TOUT, PP>;
+  auto kern = k_line6<VFLUX, SFLUX, SFV, WARPS, CTAS, NP, RK, TOUT, PP, UNR>;
   static DeviceOnce configured;
   if (configured.need()) {
     if (cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)l6_smem(WARPS)) != cudaSuccess)
@@ -776,6 +775,9 @@ static int line6_launch(const trixib200_config& c, const Dev& d, const LineOps& 
     // TRIXIB200_LINE_SHAPE=12: the ping-pong shape (3 warpgroups, flux parts serialised by a token, setmaxnreg)
     static const bool pp = getenv("TRIXIB200_LINE_SHAPE") && atoi(getenv("TRIXIB200_LINE_SHAPE")) == 12;
     if (pp && !sfv) return line6_launch_t<R, R, false, 1, 12, 8, false, true, true>(d, ops, du, u, t, elems, count, s, sm_count, rk, p2p);
+    // TRIXIB200_LINE_SHAPE=16: the default shape with the three phases unrolled
+    static const bool unr = getenv("TRIXIB200_LINE_SHAPE") && atoi(getenv("TRIXIB200_LINE_SHAPE")) == 16;
+    if (unr && !sfv) return line6_launch_t<R, R, false, 2, 4, 8, false, true, false, true>(d, ops, du, u, t, elems, count, s, sm_count, rk, p2p);
     return sfv ? line6_launch_t<R, R, true, 2, 4, 8, false, true>(d, ops, du, u, t, elems, count, s, sm_count)
                : line6_launch_t<R, R, false, 2, 4, 8, false, true>(d, ops, du, u, t, elems, count, s, sm_count, rk, p2p);
   }
