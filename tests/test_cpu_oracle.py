@@ -245,6 +245,27 @@ def test_coordinate_permutation_symmetry_3d():
     assert rel_max_err(du2m, du1) <= 1e-13
 
 
+def test_3d_flux_differencing_with_central_flux_equals_pinned_weak_form():
+    """Pins the 3D flux-differencing MACHINERY (pair loops, derivative_split, all three directions) on states that vary
+    in all three coordinates with all three velocities non-zero -- what the extruded-state test below cannot reach:
+    with flux_central the split form is the weak form, and the 3D Euler weak-form run reproduces Trixi's
+    published norms (euler_source_terms_3d in trixi_regression_norms.json). What then remains of the 3D Euler EC path is
+    the flux_ranocha formula itself, whose mass and momentum components are pinned through 2D and whose energy
+    component is the unique solution of Tadmor's condition (test_ranocha_flux_is_entropy_conservative)."""
+    kw = dict(ndim=3, equations="euler", polydeg=3, surface_flux="flux_lax_friedrichs",
+              initial_condition="weak_blast_wave", gamma=1.4, coordinates_min=(-2.0,) * 3, coordinates_max=(2.0,) * 3,
+              initial_refinement_level=2)
+    ow = O.Oracle(volume_integral="weak_form", **kw)
+    of = O.Oracle(volume_integral="flux_differencing", volume_flux="flux_central", **kw)
+    rng = np.random.default_rng(0)
+    u = ow.compute_coefficients(0.0).reshape(-1, 5).copy()
+    u[:, 0] *= 1 + 0.2 * rng.uniform(-1, 1, len(u))
+    u[:, 1:4] += 0.3 * rng.uniform(-1, 1, (len(u), 3))
+    u[:, 4] += rng.uniform(0, 1, len(u))
+    u = u.ravel()
+    assert rel_max_err(of.rhs(u, 0.0), ow.rhs(u, 0.0)) <= 1e-14
+
+
 @pytest.mark.parametrize("plane", [(0, 1), (1, 2), (0, 2)])
 def test_3d_rhs_of_extruded_2d_state_equals_pinned_2d_rhs(plane):
     """Pins the 3D code to Trixi through the 2D code: the 2D Euler EC run reproduces Trixi's published norms to 1e-16
