@@ -267,6 +267,8 @@ k_line6(const __grid_constant__ Dev d, const __grid_constant__ LineOps ops, doub
   // what the phases need to know about the faces of the CURRENT element: 4 bits per direction
   // (low face local, low face given flux, high face local, high face given flux)
   auto face_bits = [](int2 c, int dir) -> unsigned {
+    // without given-flux faces only "the x faces are local" is ever read (the 48-byte window layout of their traces)
+    if (UNR && !SFV) return dir == 0 ? ((c.x >= 0 ? 1u : 0u) | (c.y >= 0 ? 4u : 0u)) : 0u;
     return ((c.x >= 0 ? 1u : 0u) | (c.x == NB_SFV ? 2u : 0u) | (c.y >= 0 ? 4u : 0u) | (c.y == NB_SFV ? 8u : 0u)) << (4 * dir);
   };
   auto issue_block = [&](int e) {
