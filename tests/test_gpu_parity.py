@@ -488,10 +488,10 @@ def test_rhs_matches_oracle_at_baseline_sizes(name, level):
     assert abs(semi.max_dt(u_d, 0.0) / o.max_dt(u) - 1) <= 1e-13
 
 
-@pytest.mark.parametrize("shape", ["12", "16"])
+@pytest.mark.parametrize("shape", ["12", "16", "17"])
 def test_line_kernel_launch_shapes_match_oracle(shape):
     """The alternative launch shapes of k_line6 (TRIXIB200_LINE_SHAPE, read once per process -> own process): the
-    ping-pong shape and the unrolled phases that bench.py may select. du against the oracle at
+    ping-pong shape and the two code layouts (phases unrolled / z phase peeled) that bench.py may select. du against the oracle at
     levels 2 and 3 (weak blast wave and a rough state that takes both ln_mean branches), 1e-12."""
     import subprocess, sys
     root = _os.path.dirname(_os.path.dirname(_os.path.abspath(__file__)))

@@ -2,7 +2,8 @@
 between the loop head and its back edge, minus those whose source line belongs to a cold construct (the logarithmic-branch
 correction, source terms, the multi-GPU pack / flag wait) -- checked against ncu's executed-instruction counts of the default
 shape (profiles/r2_ncu_line6_l6_mix.txt: 2461 warp instructions per element pair).
-    python tools/sass_hot.py <mangled-name-substring> [--unrolled]   (--unrolled: the kernel has no phase loop)
+    python tools/sass_hot.py <mangled-name-substring> [--unrolled | --peeled]
+(--unrolled: the kernel has no phase loop; --peeled: the loop runs the y and x phases only)
 
 The single-copy shape is over-counted (its run-time switches between the three directions are counted with all arms),
 the unrolled shape is not."""
@@ -10,26 +11,31 @@ import collections, os, re, subprocess, sys, tempfile
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 so = os.path.join(ROOT, "trixicuda.jl_b200", "libtrixib200.so")
 pat = sys.argv[1]
-src = open(os.path.join(ROOT, "trixicuda.jl_b200", "csrc", "kernels_line6.cuh")).read().split("\n")
-def find(sub, start=0):
+def lines_of(name):
+    return open(os.path.join(ROOT, "trixicuda.jl_b200", "csrc", name)).read().split("\n")
+def find(src, sub, start=0):
     for i in range(start, len(src)):
         if sub in src[i]:
             return i + 1
     raise SystemExit("marker not found: " + sub)
-# cold source ranges in kernels_line6.cuh (1-based, inclusive)
-c0 = find("if (FAST && worst >= L6_ROUGH_HI)")
-c1 = find("if (PP && K0 + NP > 7)", c0) - 1
-p0 = find("if (p2p.npeers != 0) {")
-p1 = find("static_assert(!PP ||", p0) - 1
-s0 = find("if (d.src != TRIXIB200_SRC_NONE)")
-s1 = s0 + 5
-COLD6 = [(c0, c1), (p0, p1), (s0, s1)]
+# cold source ranges (1-based, inclusive): the logarithmic-branch correction and the source terms in the phase body,
+# the multi-GPU pack / flag wait in the kernel
+inc, cuh = lines_of("kernels_line6_phase.inc"), lines_of("kernels_line6.cuh")
+c0 = find(inc, "if (FAST && worst >= L6_ROUGH_HI)")
+c1 = find(inc, "if (PP && K0 + NP > 7)", c0) - 1
+s0 = find(inc, "if (d.src != TRIXIB200_SRC_NONE)")
+COLD_INC = [(c0, c1), (s0, s0 + 5)]
+p0 = find(cuh, "if (p2p.npeers != 0) {")
+p1 = find(cuh, "static_assert(!PP ||", p0) - 1
+COLD6 = [(p0, p1)]
 COLD_FILES = {"equations.cuh", "device.cuh", "kernels_warp3d.cuh"}          # exact means, face_node of the pack loop
 def cold(f, n):
     if f in COLD_FILES:
         return True
     if f == "kernels_line3d.cuh" and n >= 100:       # l3_means_exact, l3_pair_correction, l3_source
         return True
+    if f == "kernels_line6_phase.inc":
+        return any(a <= n <= b for a, b in COLD_INC)
     if f == "kernels_line6.cuh":
         return any(a <= n <= b for a, b in COLD6) or n <= 40 or (140 <= n <= 150)
     return False
@@ -84,8 +90,9 @@ print("kernel instructions", len(ins), "outer loop", outer, "inner loops", inner
 tot, ops = count(outer[0], outer[1], skip=inner[:1])
 if inner:
     ib, iops = count(*inner[0])
-    print("per-pair part", tot, "phase body", ib, "-> per element pair", tot + 3 * ib)
-    for k in iops: ops[k] += 3 * iops[k]
+    reps = 2 if "--peeled" in sys.argv else 3
+    print("per-pair part", tot, "phase body", ib, "x", reps, "-> per element pair", tot + reps * ib)
+    for k in iops: ops[k] += reps * iops[k]
 else:
     print("per element pair (phases unrolled)", tot)
 fp = sum(ops[k] for k in ("DFMA", "DMUL", "DADD"))

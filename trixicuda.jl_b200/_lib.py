@@ -11,7 +11,7 @@ import numpy as np
 _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.environ.get("TRIXIB200_LIB") or os.path.join(_HERE, "libtrixib200.so")   # override: A/B builds
 CSRC = os.path.join(_HERE, "csrc")
-SOURCES = ["runtime.cu", "kernels_analysis.cuh", "kernels_staged.cuh", "kernels_fused.cuh", "kernels_warp3d.cuh", "kernels_line3d.cuh", "kernels_line6.cuh", "equations.cuh",
+SOURCES = ["runtime.cu", "kernels_analysis.cuh", "kernels_staged.cuh", "kernels_fused.cuh", "kernels_warp3d.cuh", "kernels_line3d.cuh", "kernels_line6.cuh", "kernels_line6_phase.inc", "equations.cuh",
            "device.cuh"]
 NVCC_FLAGS = ["-O3", "-std=c++17", "-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo",
               "-shared", "-Xcompiler", "-fPIC"]

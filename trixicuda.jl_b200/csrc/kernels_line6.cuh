@@ -199,7 +199,7 @@ __device__ int l6_stagger_cycles = 0;
 // cases are compile-time) instead of one copy with run-time selection: fewer executed instructions, 2.2x the hot
 // loop's code size (TRIXIB200_LINE_SHAPE=16; bench.py times both and keeps the faster one).
 template <int VFLUX, int SFLUX, bool SFV, int WARPS, int CTAS, int NP, bool RK = false, bool TOUT = false,
-          bool PP = false, bool UNR = false>
+          bool PP = false, int UNR = 0>
 __global__ void __launch_bounds__(32 * WARPS) __maxnreg__(l6_maxnreg(WARPS, CTAS))
 k_line6(const __grid_constant__ Dev d, const __grid_constant__ LineOps ops, double* __restrict__ du,
         const double* __restrict__ u, double t, const int* __restrict__ elems, int64_t count,
@@ -268,7 +268,7 @@ k_line6(const __grid_constant__ Dev d, const __grid_constant__ LineOps ops, doub
   // (low face local, low face given flux, high face local, high face given flux)
   auto face_bits = [](int2 c, int dir) -> unsigned {
     // without given-flux faces only "the x faces are local" is ever read (the 48-byte window layout of their traces)
-    if (UNR && !SFV) return dir == 0 ? ((c.x >= 0 ? 1u : 0u) | (c.y >= 0 ? 4u : 0u)) : 0u;
+    if (UNR != 0 && !SFV) return dir == 0 ? ((c.x >= 0 ? 1u : 0u) | (c.y >= 0 ? 4u : 0u)) : 0u;
     return ((c.x >= 0 ? 1u : 0u) | (c.x == NB_SFV ? 2u : 0u) | (c.y >= 0 ? 4u : 0u) | (c.y == NB_SFV ? 8u : 0u)) << (4 * dir);
   };
   auto issue_block = [&](int e) {
@@ -421,307 +421,22 @@ k_line6(const __grid_constant__ Dev d, const __grid_constant__ LineOps ops, doub
     }
     __syncwarp();
 
-#pragma unroll(UNR ? 3 : 1)
-    for (int step = 0; step < 3; ++step) {
-      const int dir = 2 - step;
-      if (PP) relane();
-      // rows of the velocity / momentum components in slot order (slot 1 = normal component)
-      const int c0 = 1 + dir, c1 = (dir == 2) ? 1 : dir + 2, c2 = (dir == 0) ? 3 : dir;
-      const int r0 = c0 * NN, r1 = c1 * NN, r2 = c2 * NN;
-      const int2 cn = load_codes(e_next, dir);   // issued early, consumed when the trace copies are issued
-      const unsigned fb = fbits >> (4 * dir);
-      const int stp = dir == 0 ? 1 : (dir == 1 ? 4 : 21);
-      int pos[4];
-      double2* xt;                   // TILE: this lane's row of the output tile (10 chunks, stride 11)
-      auto repos = [&]() {
-        const int P = dir == 0 ? Px : (dir == 1 ? Py : Pz);
-        pos[0] = P; pos[1] = P ^ stp; pos[2] = P ^ (2 * stp); pos[3] = P ^ (3 * stp);
-        xt = reinterpret_cast<double2*>(sacc) + 11 * l16;
-      };
-      repos();
-      const int ec = e;
-      const bool valid_c = valid;
-      if (step == 2) {
-        cp_async_wait<2>();
-        __syncwarp();
+    // UNR = 0: one copy of the phase code, run-time direction. UNR = 1: three copies. UNR = 2: the z phase (no running
+    // sums to load, q still in registers) as its own copy, the y and x phases share the second one.
+    if constexpr (UNR == 2) {
+      {
+        constexpr int step = 0;
+#include "kernels_line6_phase.inc"
       }
-      // virtual line nodes: low neighbour, nodes 0..3, high neighbour; slots (rho, vn/2, vt1/2, vt2/2, p); the z phase
-      // still has its q in registers from the conversion
-      if (step > 0) {
-#pragma unroll
-      for (int m = 0; m < 4; ++m) {
-        Q[1 + m][0] = sq[pos[m]];
-        Q[1 + m][1] = sq[r0 + pos[m]];
-        Q[1 + m][2] = sq[r1 + pos[m]];
-        Q[1 + m][3] = sq[r2 + pos[m]];
-        Q[1 + m][4] = sq[4 * NN + pos[m]];
+#pragma unroll 1
+      for (int step = 1; step < 3; ++step) {
+#include "kernels_line6_phase.inc"
       }
+    } else {
+#pragma unroll(UNR == 1 ? 3 : 1)
+      for (int step = 0; step < 3; ++step) {
+#include "kernels_line6_phase.inc"
       }
-      double nbv[2][NV];
-#pragma unroll
-      for (int sd = 0; sd < 2; ++sd) {
-        const bool win = dir == 0 && (fb & (sd == 0 ? 1u : 4u));      // 48-byte windows: stride 6, data at +1 on the low face
-        const double* src = tr + face_off(dir, sd) + l16 * (win ? 6 : 5) + ((win && sd == 0) ? 1 : 0);
-        nbv[sd][0] = src[0]; nbv[sd][1] = src[c0]; nbv[sd][2] = src[c1]; nbv[sd][3] = src[c2]; nbv[sd][4] = src[4];
-      }
-      if (step == 2) {
-        // every lane has read its q: the tile becomes the landing zone of the next block
-        __syncwarp();
-        issue_block(e_next);
-        cp_async_commit();
-      }
-      l3_to_q(nbv[0], gm1, Q[0]);
-      const bool sfv_lo = SFV && (fb & 2u), sfv_hi = SFV && (fb & 8u);
-
-      // Running sums of the earlier phases. The tile keeps them in the SLOT order of the phase that wrote them (static
-      // rows); with the phases running z, y, x a phase's slot 1 + s is the previous phase's slot 1 + (s + 2) % 3. They
-      // are the initial values of this phase's sums (no separate add), loaded early; the phase's result goes back to
-      // the same entries in its own slot order (each lane touches only its own nodes).
-      // Tile layout: slots (0, 1) and (2, 3) as 16-byte pairs [2][64] double2, slot 4 as [64] doubles behind them: three
-      // shared-memory accesses per node instead of five (16 lanes x 16 B at distinct swizzled positions = the minimal
-      // two wavefronts).
-      auto load_old = [&](int m, double* a) {
-        if (step > 0) {
-          const double2* p2 = reinterpret_cast<const double2*>(sacc) + pos[m];
-          const double2 s01 = p2[0], s23 = p2[NN];
-          a[0] = s01.x; a[2] = s01.y; a[3] = s23.x; a[1] = s23.y; a[4] = sacc[4 * NN + pos[m]];
-        } else {
-#pragma unroll
-          for (int v = 0; v < NV; ++v) a[v] = 0.0;
-        }
-      };
-      // a finished node: handed to the next phase, or (x phase) scaled by the Jacobian (+ source terms)
-      auto hand_over = [&](int m, double* a) {
-        if (step < 2) {
-          double2* p2 = reinterpret_cast<double2*>(sacc) + pos[m];
-          p2[0] = make_double2(a[0], a[1]);
-          p2[NN] = make_double2(a[2], a[3]);
-          sacc[4 * NN + pos[m]] = a[4];
-        } else {
-          const double scale = RK ? -inv_jac * rk.dt : -inv_jac;
-#pragma unroll
-          for (int v = 0; v < NV; ++v) a[v] *= scale;
-          if (d.src != TRIXIB200_SRC_NONE) {
-            const L3Vec5 sv = l3_source(&d, ec, m + 4 * l16, m, la, lb, inv_jac, t, u);
-#pragma unroll
-            for (int v = 0; v < NV; ++v) a[v] = RK ? fma(rk.dt, sv.v[v], a[v]) : a[v] + sv.v[v];
-          }
-        }
-      };
-      if (RK && step == 1) {
-        // one phase ahead: pull the 20 + 20 lines of the element's old tmp / u_in into L1, so that the two fetches of
-        // the x phase are L1 hits (tmp comes from DRAM, u_in from L2: it was read through cp.async three phases ago)
-        const char* bu = reinterpret_cast<const char*>(u + (size_t)NV * NN * ec);
-        const char* bt = reinterpret_cast<const char*>(rk.tmp + (size_t)NV * NN * ec);
-        asm volatile("prefetch.global.L1 [%0];" ::"l"(bu + 128 * l16));
-        if (rk.a != 0.0) asm volatile("prefetch.global.L1 [%0];" ::"l"(bt + 128 * l16));
-        if (l16 < 4) {
-          asm volatile("prefetch.global.L1 [%0];" ::"l"(bu + 128 * (16 + l16)));
-          if (rk.a != 0.0) asm volatile("prefetch.global.L1 [%0];" ::"l"(bt + 128 * (16 + l16)));
-        }
-      }
-
-      // ---- the 8 pair fluxes of the line in batches of NP (reference dg_3d_kernel.jl:188-257 evaluates 12 volume
-      // fluxes per node, and the interface fluxes in two more kernels); a node is handed over as soon as its last pair
-      // is in: node 0 after pair 3, node 1 after pair 5, nodes 2 and 3 after pair 7
-      double acc[4][NV];
-      int seed_s[8], seed_t[8];
-      if (PP) {
-        l3_to_q(nbv[1], gm1, Q[5]);    // all six virtual nodes are ready before the token is taken
-#ifdef L6_PP_SEED_EARLY
-        if (FAST) l6_seeds<8>(Q, seed_s, seed_t);
-#endif
-#ifdef L6_PP_ACC_EARLY
-        // the running sums too (40 more registers live across the wait)
-        load_old(0, acc[0]); load_old(1, acc[1]); load_old(2, acc[2]); load_old(3, acc[3]);
-#endif
-        l6_bar_sync(l6_pp_bar(wg, 3 * it + step), 256);      // token: this warpgroup's turn on the FP64 pipe
-        l6_reg_inc<L6_PP_HI>();
-#ifndef L6_PP_ACC_EARLY
-        load_old(0, acc[0]); load_old(1, acc[1]); load_old(2, acc[2]); load_old(3, acc[3]);
-#endif
-      } else {
-        load_old(0, acc[0]);
-      }
-      auto batch = [&](auto k0_tag) {
-        constexpr int K0 = decltype(k0_tag)::value;
-        if (!PP && K0 + NP > 7) l3_to_q(nbv[1], gm1, Q[5]);   // converted when its pair comes up
-        double F[NP][NV];
-        unsigned hw[NP];
-#ifdef L6_PP_SEED_EARLY
-        l6_fluxes<FAST, K0, NP, PP && FAST>(Q, vflux, sflux, prm, F, hw, seed_s, seed_t);
-#else
-        l6_fluxes<FAST, K0, NP>(Q, vflux, sflux, prm, F, hw);
-#endif
-        if (SFV && K0 == 0) {
-          if (sfv_lo) hw[0] = 0;      // the trace IS the flux: nothing to correct
-#pragma unroll
-          for (int v = 0; v < NV; ++v) F[0][v] = sfv_lo ? nbv[0][v] : F[0][v];
-        }
-        if (SFV && K0 + NP > 7) {
-          if (sfv_hi) hw[7 - K0] = 0;
-#pragma unroll
-          for (int v = 0; v < NV; ++v) F[7 - K0][v] = sfv_hi ? nbv[1][v] : F[7 - K0][v];
-        }
-        unsigned worst = hw[0];
-#pragma unroll
-        for (int k = 1; k < NP; ++k) worst = max(worst, hw[k]);
-        if (!PP) {
-          if (K0 <= 1 && K0 + NP > 1) load_old(1, acc[1]);
-          if (K0 <= 2 && K0 + NP > 2) load_old(2, acc[2]);
-          if (K0 <= 3 && K0 + NP > 3) load_old(3, acc[3]);
-        }
-        auto accumulate = [&](int k, int v) {
-          const int kk = K0 + k;
-          if (kk == 0) acc[0][v] = fma(-ops.factor_1, F[k][v], acc[0][v]);
-          else if (kk == 7) acc[3][v] = fma(ops.factor_2, F[k][v], acc[3][v]);
-          else {
-            const int x = L6_PA[kk] - 1, y = L6_PB[kk] - 1;
-            acc[x][v] = fma(ops.ds[x + 4 * y], F[k][v], acc[x][v]);
-            acc[y][v] = fma(ops.ds[y + 4 * x], F[k][v], acc[y][v]);
-          }
-        };
-#pragma unroll
-        for (int k = 0; k < NP; ++k) {
-#pragma unroll
-          for (int v = 0; v < NV; ++v) accumulate(k, v);
-          // PP: the next warpgroup is woken a little before this one gives its registers back, so that its wake-up
-          // latency is hidden behind the last accumulations
-          if (PP && L6_PP_TOKENS == 1 && K0 + k == L6_PP_ARRIVE_K)
-            l6_bar_arrive_after(l6_pp_bar((wg + L6_PP_TOKENS) % 3, (3 * (3 * it + step) + wg + L6_PP_TOKENS) / 3), 256,
-                                acc[L6_PB[K0 + k] - 1 > 3 ? 3 : L6_PB[K0 + k] - 1][NV - 1]);
-        }
-        if (FAST && worst >= L6_ROUGH_HI) {
-#pragma unroll
-          for (int k = 0; k < NP; ++k)
-            if (hw[k] >= L6_ROUGH_HI) {
-              const int kk = K0 + k;
-              L6Pair pp;
-#pragma unroll
-              for (int v = 0; v < NV; ++v) { pp.a[v] = Q[L6_PA[kk]][v]; pp.b[v] = Q[L6_PB[kk]][v]; }
-              const L3Vec5 df = l6_pair_correction(pp, prm.inv_gm1);
-#pragma unroll
-              for (int v = 0; v < NV; ++v) {
-                if (kk == 0) acc[0][v] = fma(-ops.factor_1, df.v[v], acc[0][v]);
-                else if (kk == 7) acc[3][v] = fma(ops.factor_2, df.v[v], acc[3][v]);
-                else {
-                  const int x = L6_PA[kk] - 1, y = L6_PB[kk] - 1;
-                  acc[x][v] = fma(ops.ds[x + 4 * y], df.v[v], acc[x][v]);
-                  acc[y][v] = fma(ops.ds[y + 4 * x], df.v[v], acc[y][v]);
-                }
-              }
-            }
-        }
-        if (PP && K0 + NP > 7) {
-          // the 8 fluxes are accumulated: registers and token go to the next warpgroup (warpgroup 0
-          // absorbs the last one behind the loop)
-#if L6_PP_TOKENS == 1
-          if (L6_PP_ARRIVE_K >= 8)
-            l6_bar_arrive(l6_pp_bar((wg + L6_PP_TOKENS) % 3, (3 * (3 * it + step) + wg + L6_PP_TOKENS) / 3), 256);
-          l6_reg_dec<L6_PP_LO>();
-#else
-          l6_reg_dec<L6_PP_LO>();        // with two tokens the registers must be back before the next one is let in
-          l6_bar_arrive(l6_pp_bar((wg + L6_PP_TOKENS) % 3, (3 * (3 * it + step) + wg + L6_PP_TOKENS) / 3), 256);
-#endif
-          relane();
-          repos();
-        }
-        // finished nodes
-        if (K0 <= 3 && K0 + NP > 3) {
-          hand_over(0, acc[0]);
-          if (step == 2) {
-            if (TILE) {
-              __syncwarp();      // every lane has taken its running sums out of the tile region
-              xt[0] = make_double2(acc[0][0], acc[0][1]);
-              xt[1] = make_double2(acc[0][2], acc[0][3]);
-            } else if (valid_c) {
-              double2* o = reinterpret_cast<double2*>(du + (size_t)NV * NN * ec + 20 * l16);
-              __stcs(&o[0], make_double2(acc[0][0], acc[0][1]));
-              __stcs(&o[1], make_double2(acc[0][2], acc[0][3]));
-            }
-          }
-        }
-        if (K0 <= 5 && K0 + NP > 5) {
-          hand_over(1, acc[1]);
-          if (step == 2) {
-            if (TILE) {
-              xt[2] = make_double2(acc[0][4], acc[1][0]);
-              xt[3] = make_double2(acc[1][1], acc[1][2]);
-              xt[4] = make_double2(acc[1][3], acc[1][4]);
-            } else if (valid_c) {
-              double2* o = reinterpret_cast<double2*>(du + (size_t)NV * NN * ec + 20 * l16);
-              __stcs(&o[2], make_double2(acc[0][4], acc[1][0]));
-              __stcs(&o[3], make_double2(acc[1][1], acc[1][2]));
-              __stcs(&o[4], make_double2(acc[1][3], acc[1][4]));
-            }
-          }
-        }
-        if (K0 + NP > 7) {
-          hand_over(2, acc[2]);
-          hand_over(3, acc[3]);
-          if (step == 2) {
-            if (TILE) {
-              xt[5] = make_double2(acc[2][0], acc[2][1]);
-              xt[6] = make_double2(acc[2][2], acc[2][3]);
-              xt[7] = make_double2(acc[2][4], acc[3][0]);
-              xt[8] = make_double2(acc[3][1], acc[3][2]);
-              xt[9] = make_double2(acc[3][3], acc[3][4]);
-            } else if (valid_c) {
-              double2* o = reinterpret_cast<double2*>(du + (size_t)NV * NN * ec + 20 * l16);
-              __stcs(&o[5], make_double2(acc[2][0], acc[2][1]));
-              __stcs(&o[6], make_double2(acc[2][2], acc[2][3]));
-              __stcs(&o[7], make_double2(acc[2][4], acc[3][0]));
-              __stcs(&o[8], make_double2(acc[3][1], acc[3][2]));
-              __stcs(&o[9], make_double2(acc[3][3], acc[3][4]));
-            }
-          }
-        }
-      };
-      batch(std::integral_constant<int, 0>{});
-      if constexpr (NP <= 4) batch(std::integral_constant<int, NP>{});
-      if constexpr (NP <= 2) { batch(std::integral_constant<int, 2 * NP>{}); batch(std::integral_constant<int, 3 * NP>{}); }
-      if (TILE && step == 2) {
-        // second pass over whole 16-byte chunks c = l16 + 16 j of the element block (tile position c + c / 10):
-        // plain du store, or the 2N Runge-Kutta stage  tmp = a tmp + dt du;  u_out = u_in + b tmp
-        __syncwarp();
-        const double2* tile = reinterpret_cast<const double2*>(sacc);
-        double2* po = reinterpret_cast<double2*>(du + (size_t)NV * NN * ec);
-        double2* pt = RK ? reinterpret_cast<double2*>(rk.tmp + (size_t)NV * NN * ec) : nullptr;
-        const double2* pu = reinterpret_cast<const double2*>(u + (size_t)NV * NN * ec);
-#pragma unroll
-        for (int r = 0; r < 2; ++r) {
-          double2 xv[5], tv[5], uv[5];
-#pragma unroll
-          for (int j = 0; j < 5; ++j) {
-            const int c = l16 + 16 * (5 * r + j);
-            xv[j] = tile[c + c / 10];
-            if (RK) {
-              uv[j] = pu[c];                                                   // L1 hits: prefetched a phase ago
-              tv[j] = rk.a != 0.0 ? pt[c] : make_double2(0.0, 0.0);
-            }
-          }
-#pragma unroll
-          for (int j = 0; j < 5; ++j) {
-            const int c = l16 + 16 * (5 * r + j);
-            if (RK) {
-              const double t0 = fma(rk.a, tv[j].x, xv[j].x), t1 = fma(rk.a, tv[j].y, xv[j].y);
-              if (valid_c) {
-                __stcs(pt + c, make_double2(t0, t1));
-                __stcs(po + c, make_double2(fma(rk.b, t0, uv[j].x), fma(rk.b, t1, uv[j].y)));
-              }
-            } else if (valid_c) {
-              __stcs(po + c, xv[j]);
-            }
-          }
-        }
-      }
-      __syncwarp();   // traces consumed, running sums visible
-      if (pr_next >= p2p.first_cut_pair) wait_halo();
-      if (dir == 0) issue_traces(D0{}, e_next, cn.x, cn.y);
-      else if (dir == 1) issue_traces(D1{}, e_next, cn.x, cn.y);
-      else issue_traces(D2{}, e_next, cn.x, cn.y);
-      cp_async_commit();
-      fbits_next |= face_bits(cn, dir);
     }
     e = e_next; valid = valid_next; fbits = fbits_next;
   }
@@ -736,7 +451,7 @@ k_line6(const __grid_constant__ Dev d, const __grid_constant__ LineOps ops, doub
 // kernel's time follows the SUM of the issue costs of its instructions, not the occupancy: 1 warp per scheduler already
 // reaches 70 % of the throughput of 2, and 3 add nothing (profiles/r1_line6_notes.md).
 template <int VFLUX, int SFLUX, bool SFV, int CTAS, int WARPS, int NP, bool RK = false, bool TOUT = false,
-          bool PP = false, bool UNR = false>
+          bool PP = false, int UNR = 0>
 static int line6_launch_t(const Dev& d, const LineOps& ops, double* du, const double* u, double t, const int* elems,
                           int64_t count, cudaStream_t stream, int sm_count, const RkArgs& rk = RkArgs{nullptr, 0, 0, 0},
                           const P2PArgs& p2p = P2PArgs{}) {
@@ -779,7 +494,10 @@ static int line6_launch(const trixib200_config& c, const Dev& d, const LineOps& 
     if (pp && !sfv) return line6_launch_t<R, R, false, 1, 12, 8, false, true, true>(d, ops, du, u, t, elems, count, s, sm_count, rk, p2p);
     // TRIXIB200_LINE_SHAPE=16: the default shape with the three phases unrolled
     static const bool unr = getenv("TRIXIB200_LINE_SHAPE") && atoi(getenv("TRIXIB200_LINE_SHAPE")) == 16;
-    if (unr && !sfv) return line6_launch_t<R, R, false, 2, 4, 8, false, true, false, true>(d, ops, du, u, t, elems, count, s, sm_count, rk, p2p);
+    if (unr && !sfv) return line6_launch_t<R, R, false, 2, 4, 8, false, true, false, 1>(d, ops, du, u, t, elems, count, s, sm_count, rk, p2p);
+    // TRIXIB200_LINE_SHAPE=17: the z phase peeled, the y and x phases in one copy
+    static const bool peel = getenv("TRIXIB200_LINE_SHAPE") && atoi(getenv("TRIXIB200_LINE_SHAPE")) == 17;
+    if (peel && !sfv) return line6_launch_t<R, R, false, 2, 4, 8, false, true, false, 2>(d, ops, du, u, t, elems, count, s, sm_count, rk, p2p);
     return sfv ? line6_launch_t<R, R, true, 2, 4, 8, false, true>(d, ops, du, u, t, elems, count, s, sm_count)
                : line6_launch_t<R, R, false, 2, 4, 8, false, true>(d, ops, du, u, t, elems, count, s, sm_count, rk, p2p);
   }
