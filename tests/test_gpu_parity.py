@@ -488,6 +488,29 @@ def test_rhs_matches_oracle_at_baseline_sizes(name, level):
     assert abs(semi.max_dt(u_d, 0.0) / o.max_dt(u) - 1) <= 1e-13
 
 
+def test_save_solution_callback_in_a_run(tmp_path):
+    """The reference example's callback set incl. SaveSolutionCallback (reference examples/euler_ec_3d.jl:38-49): the
+    run writes mesh.h5, the initial and the final solution in Trixi's layout, and the final file holds cons2prim of the
+    state the run returns."""
+    import trixib200 as T
+    from trixib200 import solution_file as S
+    c = dict(CASES["c5_euler_ec_3d"], level=2)
+    semi = make_semi(c)
+    ode = T.semidiscretizeGPU(semi, (0.0, 0.05))
+    save = T.SaveSolutionCallback(interval=100, save_initial_solution=True, save_final_solution=True,
+                                  solution_variables=T.cons2prim, output_directory=str(tmp_path))
+    sol = T.solve(ode, T.CarpenterKennedy2N54(williamson_condition=False), dt=1.0,
+                  callback=T.CallbackSet(T.StepsizeCallback(cfl=1.3), save))
+    assert [ts for ts, _ in save.files] == [0, sol.nsteps] and _os.path.exists(str(tmp_path / "mesh.h5"))
+    attrs, data, names, _ = S.load_solution_file(save.files[-1][1])
+    assert attrs["n_elements"] == semi.nelements and attrs["timestep"] == sol.nsteps and abs(attrs["time"] - 0.05) < 1e-15
+    assert names == ["rho", "v1", "v2", "v3", "p"]
+    u = sol.u[-1].cpu().numpy().reshape(semi.nelements, 4, 4, 4, 5)
+    assert np.abs(data - S.cons2prim(u, semi.equations)).max() <= 1e-14
+    _, init, _, _ = S.load_solution_file(save.files[0][1])
+    assert np.abs(init - S.cons2prim(ode.u0.cpu().numpy().reshape(u.shape), semi.equations)).max() <= 1e-14
+
+
 @pytest.mark.parametrize("shape", ["12", "16", "17"])
 def test_line_kernel_launch_shapes_match_oracle(shape):
     """The alternative launch shapes of k_line6 (TRIXIB200_LINE_SHAPE, read once per process -> own process): the

@@ -28,6 +28,8 @@ from .semidiscretization import (SemidiscretizationHyperbolicGPU, semidiscretize
 from . import semidiscretization as _semi_mod
 from .ode import (CarpenterKennedy2N54, StepsizeCallback, AnalysisCallback, CallbackSet, solve, calc_error_norms,
                   calculate_dt)
+from .solution_file import (SaveSolutionCallback, save_solution_file, save_mesh_file, load_solution_file, cons2prim,
+                            varnames)
 calc_error_norms_gpu = _semi_mod.calc_error_norms
 
 __all__ = [n for n in dir() if not n.startswith("_")]

@@ -116,9 +116,13 @@ def solve(ode, alg=None, dt=1.0, callback=None, maxiters=10 ** 9, fused_stages=F
     t, t_end = float(ode.tspan[0]), float(ode.tspan[1])
     cb = callback if isinstance(callback, CallbackSet) else CallbackSet(*( [callback] if callback else [] ))
     step_cb, ana_cb = cb.find(StepsizeCallback), cb.find(AnalysisCallback)
+    from .solution_file import SaveSolutionCallback
+    save_cb = cb.find(SaveSolutionCallback)
     nsteps = 0
     if ana_cb is not None:
         ana_cb(u, t)
+    if save_cb is not None:
+        save_cb(u, t, 0.0, 0, semi)
     while t < t_end and nsteps < maxiters:
         if step_cb is not None:
             dt = calculate_dt(u, t, step_cb.cfl, semi)
@@ -136,7 +140,11 @@ def solve(ode, alg=None, dt=1.0, callback=None, maxiters=10 ** 9, fused_stages=F
         nsteps += 1
         if ana_cb is not None and ana_cb.interval > 0 and nsteps % ana_cb.interval == 0:
             ana_cb(u, t)
+        if save_cb is not None:
+            save_cb(u, t, dt, nsteps, semi)
     if ana_cb is not None:
         ana_cb(u, t)
+    if save_cb is not None:
+        save_cb(u, t, dt, nsteps, semi, finished=True)
     sol = Solution(u, t, nsteps)
     return sol
