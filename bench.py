@@ -331,6 +331,18 @@ def build_semi(config, level, rank, nranks, comm_id, device):
                                              node_coordinates=False, **kw)
 
 
+def build_semi_flags(level, device, staged_only):
+    """Config 5 on one GPU at `level`, default fused path or the staged (one kernel per reference stage) path."""
+    import trixib200 as T
+    basis = T.LobattoLegendreBasisGPU(3)
+    eq = T.CompressibleEulerEquations3D(1.4)
+    solver = T.DGSEMGPU(polydeg=3, surface_flux=T.flux_ranocha, basis=basis,
+                        volume_integral=T.VolumeIntegralFluxDifferencing(T.flux_ranocha))
+    mesh = T.TreeMesh((-2.0,) * 3, (2.0,) * 3, initial_refinement_level=level, periodicity=True, n_cells_max=10 ** 9)
+    return T.SemidiscretizationHyperbolicGPU(mesh, eq, T.initial_condition_weak_blast_wave, solver, device=device,
+                                             staged_only=staged_only, node_coordinates=False)
+
+
 def parity_check(args, rank, world, comm_id, local_rank, dist, dev):
     """du of the product against the CPU oracle on the same mesh, equations and IC before anything is timed: config 5 at
     level 5 (the oracle needs 33 ms there), configs 1-4 at their full size; N > 1: every rank checks its Morton range."""
@@ -546,6 +558,32 @@ def run_ours(args):
             T.rhs_gpu_(du, u, semi, 0.0)
         except Exception as ex:  # context only: never fail the bench line over it
             extras = {"error": repr(ex)}
+    if args.config == 5 and world == 1:
+        # Context (BASELINE.json: "for context, TrixiCUDA.jl's existing CUDA.jl kernels"): those need Julia, which this
+        # image does not have. What can be timed is the reference's STRUCTURE on the same GPU: the staged path runs one
+        # kernel per reference stage (volume integral, prolong2interfaces, interface flux, surface integral +
+        # Jacobian) and materialises interfaces.u / surface_flux_values in Trixi's layouts, exactly the pipeline of
+        # reference src/solvers/dg_3d.jl:895-925 -- but with this repo's kernels (symmetric pairs, coalesced), so it
+        # is a LOWER bound on what the reference's kernels cost. Level 6: the containers of level 7 would need 34 GB.
+        try:
+            ctx = {}
+            for name, staged in (("fused_ms", False), ("staged_pipeline_ms", True)):
+                s6 = build_semi_flags(6, local_rank, staged)
+                u6 = s6.compute_coefficients_gpu(0.0, on_device=True)
+                d6 = s6.new_vector()
+                for _ in range(3):
+                    s6.rhs(d6, u6, 0.0)
+                torch.cuda.synchronize()
+                l6 = s6.launch_count()
+                ctx[name] = s6.time_rhs(d6, u6, 0.0, 10) / 10
+                ctx[name.replace("_ms", "_launches_per_rhs")] = (s6.launch_count() - l6) / 10
+                del s6, u6, d6
+                torch.cuda.empty_cache()
+            ctx["note"] = ("level 6 (16.8 M DOF): one fused launch vs one kernel per reference stage with materialised "
+                           "interfaces.u / surface_flux_values (the reference's pipeline with this repo's kernels)")
+            extras["reference_structure_context"] = ctx
+        except Exception as ex:
+            extras["reference_structure_context"] = {"error": repr(ex)}
     if per_call:
         extras["us_per_rhs_median"] = per_call[len(per_call) // 2] * 1e3
         extras["us_per_rhs_min"] = per_call[0] * 1e3
