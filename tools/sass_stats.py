@@ -1,6 +1,6 @@
 """Static SASS statistics of one kernel in libtrixib200.so: code size, opcode mix, encoded stall counts."""
 import collections, re, subprocess, sys
-pat = sys.argv[1] if len(sys.argv) > 1 else "k_line3dILi5ELi5ELi4"
+pat = sys.argv[1] if len(sys.argv) > 1 else "k_line6ILi5ELi5ELb0ELi4ELi2ELi8ELb0ELb1ELb0ELi0E"
 so = sys.argv[2] if len(sys.argv) > 2 else "trixicuda.jl_b200/libtrixib200.so"
 out = subprocess.run(["cuobjdump", "-sass", so], capture_output=True, text=True).stdout.split("\n")
 ins, on = [], False

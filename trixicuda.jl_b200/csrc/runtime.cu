@@ -845,15 +845,9 @@ static int rhs_staged(trixib200_handle* h, double* du, const double* u, double t
   return 0;
 }
 
-// one launch of the best fused kernel over a list (or, with elems == nullptr, the first `count`) of elements
-static bool line_gen5() {
-  // TRIXIB200_LINE_KERNEL=5 selects the previous generation of the line-owner kernel (A/B measurements)
-  static const bool gen5 = getenv("TRIXIB200_LINE_KERNEL") && atoi(getenv("TRIXIB200_LINE_KERNEL")) == 5;
-  return gen5;
-}
 // can rhs! + 2N Runge-Kutta stage run as ONE launch (k_line6<..., RK = true>) on these vectors?
 static bool rk_fusable(const trixib200_handle* h, const double* u_out, const double* u_in, const double* tmp) {
-  return h->fused && h->line3d && !line_gen5() &&
+  return h->fused && h->line3d &&
          ((((uintptr_t)u_out) | ((uintptr_t)u_in) | ((uintptr_t)tmp)) & 15) == 0;
 }
 
@@ -876,9 +870,7 @@ static int fused_launch_any(trixib200_handle* h, double* du, const double* u, do
   }
   const bool w3 = h->warp3d && ((((uintptr_t)u) | ((uintptr_t)du)) & 15) == 0;
   const bool l3 = w3 && h->line3d;
-  const bool gen5 = line_gen5();
-  int rc = (l3 && !gen5) ? line6_launch(h->cfg, d, h->line_ops, du, u, t, elems, count, h->stream, h->sm_count)
-         : l3 ? line3d_launch(h->cfg, d, h->line_ops, du, u, t, elems, count, h->stream, h->sm_count)
+  int rc = l3 ? line6_launch(h->cfg, d, h->line_ops, du, u, t, elems, count, h->stream, h->sm_count)
          : w3 ? warp3d_launch(h->cfg, d, du, u, t, elems, count, h->stream, h->sm_count)
               : fused_launch(h->cfg, d, du, u, t, elems, count, h->stream, h->sm_count);
   if (rc) return fail(rc, "fused launch failed");
@@ -908,7 +900,6 @@ static int rhs_fused(trixib200_handle* h, double* du, const double* u, double t,
   if (h->p2p.enabled && h->cfg.nranks > 1 && h->p2p.mesh_ok) {
     if ((((uintptr_t)u) | ((uintptr_t)du) | (rk ? (uintptr_t)rk->tmp : 0)) & 15)
       return fail(TRIXIB200_EINVAL, "multi-GPU rhs!: vectors must be 16-byte aligned");
-    if (line_gen5()) return fail(TRIXIB200_EUNSUPPORTED, "TRIXIB200_LINE_KERNEL=5 has no in-kernel halo exchange");
     auto& P = h->p2p;
     const unsigned long long epoch = ++P.epoch;
     const int par = (int)(epoch & 1);
