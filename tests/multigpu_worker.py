@@ -74,8 +74,12 @@ def main():
             assert np.array_equal(du_h, got), (name, staged, "rhs_host")
             del semi
         dist.barrier()
+        if rank == 0:
+            print(f"[multigpu] {name} done", flush=True)      # (a hang is then attributable to one case)
     print("MULTIGPU_OK", rank, flush=True)
-    dist.destroy_process_group()
+    dist.barrier()
+    sys.stdout.flush()
+    os._exit(0)      # like bench.py: leave without communicator / IPC teardown in garbage-collection order
 
 
 if __name__ == "__main__":
