@@ -584,6 +584,16 @@ def run_ours(args):
             extras["reference_structure_context"] = ctx
         except Exception as ex:
             extras["reference_structure_context"] = {"error": repr(ex)}
+    if world > 1:
+        try:
+            extras["multi_gpu"] = {
+                "halo_exchange": ("inside the kernel: peers' receive buffers mapped with CUDA IPC, traces stored over "
+                                  "NVLink, flag words (one launch per rhs!)") if semi.size("p2p_halo") else
+                                 "k_pack_halo + grouped ncclSend/ncclRecv on a communication stream, two launches",
+                "peers_of_rank0": semi.size("npeers"), "halo_faces_of_rank0": semi.size("nhalo_faces"),
+                "elements_of_rank0": semi.nelements, "launches_per_rhs": launches / K}
+        except Exception as ex:
+            extras["multi_gpu"] = {"error": repr(ex)}
     if per_call:
         extras["us_per_rhs_median"] = per_call[len(per_call) // 2] * 1e3
         extras["us_per_rhs_min"] = per_call[0] * 1e3
