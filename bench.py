@@ -381,8 +381,8 @@ PROBE_CACHE = "/tmp/trixib200_line_shape_probe.json"
 def pick_line_shape(device_index):
     """Config 5 runs the line-owner kernel k_line6, which exists in two launch shapes that differ only in code layout
     (kernels_line6.cuh, TRIXIB200_LINE_SHAPE). Before anything is timed, each shape is run in its own process
-    (tools/line_check.py: du against the CPU oracle at levels 2 and 3 -- odd element counts per warp, both ln_mean
-    branches -- then CUDA-event timing at level 6); the fastest shape that passed the parity check is exported as
+    (tools/line_check.py: du against the CPU oracle at levels 2, 3 and 5 -- odd element counts per warp, several
+    element pairs per persistent warp, both ln_mean branches -- then CUDA-event timing at level 6); the fastest shape that passed the parity check is exported as
     TRIXIB200_LINE_SHAPE for this run. A shape that fails, crashes or times out is dropped; with no usable probe the
     default shape stays. Returns what was measured (goes into the JSON line)."""
     import re
@@ -411,10 +411,10 @@ def pick_line_shape(device_index):
         if shape != "default":
             env["TRIXIB200_LINE_SHAPE"] = shape
         try:
-            out = subprocess.run([sys.executable, os.path.join(ROOT, "tools", "line_check.py"), "2", "3", "--", "6"],
+            out = subprocess.run([sys.executable, os.path.join(ROOT, "tools", "line_check.py"), "2", "3", "5", "--", "6"],
                                  capture_output=True, text=True, timeout=240, env=env)
             ms = re.findall(r"level 6: rhs ([0-9.]+) ms", out.stdout)
-            ok = out.returncode == 0 and "FAIL" not in out.stdout and out.stdout.count(" ok") >= 4 and ms
+            ok = out.returncode == 0 and "FAIL" not in out.stdout and out.stdout.count(" ok") >= 6 and ms
             res[shape] = {"parity_ok": bool(ok), "ms_level6": float(ms[-1]) if ms else None}
         except Exception as ex:       # timeout, missing tool: the shape is simply not a candidate
             res[shape] = {"parity_ok": False, "ms_level6": None, "error": type(ex).__name__}
