@@ -191,10 +191,6 @@ TB_D void l6_bar_arrive_after(int id, int n, double dep) {
 #define L6_PP_ARRIVE_K 5     // the token is passed on when pair K of the 8 has been accumulated (8: behind setmaxnreg.dec)
 #endif
 
-// A/B knob (TRIXIB200_LINE_STAGGER=cycles): the second half of the grid (the CTAs that share an SM with the first
-// half) starts that many cycles late, so that the two warps of a scheduler are not in the same part of an iteration.
-__device__ int l6_stagger_cycles = 0;
-
 // UNR: the three phases as three copies of the code (direction, slot rotation and the first / last phase special
 // cases are compile-time) instead of one copy with run-time selection: fewer executed instructions, 2.2x the hot
 // loop's code size (TRIXIB200_LINE_SHAPE=16; bench.py times both and keeps the faster one).
@@ -240,13 +236,6 @@ k_line6(const __grid_constant__ Dev d, const __grid_constant__ LineOps ops, doub
     Px = 16 * lb + 4 * (la ^ lb) + lb; Py = 20 * lb + (la ^ lb); Pz = l16;
   };
   relane();
-  if (!PP && CTAS > 1) {
-    const int stg = l6_stagger_cycles;
-    if (stg > 0 && 2 * blockIdx.x >= gridDim.x) {
-      const long long t0 = clock64();
-      while (clock64() - t0 < stg) {}
-    }
-  }
   const EqPrm prm = d.prm;
   const double gm1 = prm.gamma - 1;
   const int vflux = (VFLUX >= 0) ? VFLUX : d.vol_flux;
@@ -463,11 +452,6 @@ static int line6_launch_t(const Dev& d, const LineOps& ops, double* du, const do
     cudaFuncSetAttribute(kern, cudaFuncAttributePreferredSharedMemoryCarveout, 100);
   }
   if (count <= 0) return 0;
-  static DeviceOnce staggered;
-  if (staggered.need()) {
-    const int stg = getenv("TRIXIB200_LINE_STAGGER") ? atoi(getenv("TRIXIB200_LINE_STAGGER")) : 0;
-    if (stg > 0) cudaMemcpyToSymbol(l6_stagger_cycles, &stg, sizeof(int));
-  }
   const int64_t npairs = (count + 1) / 2;
   const int64_t want = (npairs + WARPS - 1) / WARPS;
   const unsigned blocks = (unsigned)std::min<int64_t>(want, (int64_t)sm_count * CTAS);
