@@ -412,7 +412,7 @@ def pick_line_shape(device_index):
             env["TRIXIB200_LINE_SHAPE"] = shape
         try:
             out = subprocess.run([sys.executable, os.path.join(ROOT, "tools", "line_check.py"), "2", "3", "5", "--", "6"],
-                                 capture_output=True, text=True, timeout=240, env=env)
+                                 capture_output=True, text=True, timeout=150, env=env)
             ms = re.findall(r"level 6: rhs ([0-9.]+) ms", out.stdout)
             ok = out.returncode == 0 and "FAIL" not in out.stdout and out.stdout.count(" ok") >= 6 and ms
             res[shape] = {"parity_ok": bool(ok), "ms_level6": float(ms[-1]) if ms else None}
