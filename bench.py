@@ -420,6 +420,9 @@ def pick_line_shape(device_index):
             res[shape] = {"parity_ok": False, "ms_level6": None, "error": type(ex).__name__}
     good = {k: v["ms_level6"] for k, v in res.items() if v["parity_ok"]}
     chosen = min(good, key=good.get) if good else "default"
+    # the default shape is the one the whole GPU test suite runs: another one has to beat it by more than timing noise
+    if chosen != "default" and "default" in good and good[chosen] > 0.98 * good["default"]:
+        chosen = "default"
     if chosen != "default":
         os.environ["TRIXIB200_LINE_SHAPE"] = chosen
     out = {"chosen": chosen, "probes": res, "what": LINE_SHAPES, "key": key}
